@@ -1,0 +1,185 @@
+"""Pins the C restatement (oracle/dabmod_oracle.c) against the UNMODIFIED
+reference code (oracle/_ref/libdabmod_ref.so, built from /root/reference by
+oracle/Makefile).  Runs wherever the reference library exists: in the build
+container it is compiled by __graft_entry__.build(); on the GPU box the
+prebuilt .so travels with the snapshot.
+
+Tolerances: bit-exact where the arithmetic is integer/copy/identical float32
+ops; 1e-6 relative RMS where a float32 FFT library (reference: KISS-float
+behind the fftw3 shim) meets our double-precision DFT -- 10x inside the 1e-5
+budget of BASELINE.json.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_rms, write_taps_file, write_poly_file, write_lut_file
+from oracle import oracle, refwrap
+
+pytestmark = [pytest.mark.ref,
+              pytest.mark.skipif(not refwrap.available(), reason="reference library not built")]
+
+FFT_TOL = 1e-6
+
+
+def bits_for(rng, mode, n):
+    return rng.integers(0, 256, (n, refwrap.TF_BYTES[mode]), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("stage", ["qpsk", "freq", "diff", "mux"])
+def test_integer_stages_bit_exact(rng, mode, stage):
+    bits = bits_for(rng, mode, 2)
+    ref = refwrap.RefChain(mode=mode, stop_after=stage).run(bits)
+    ora = oracle.OracleChain(mode=mode).run(bits, stage=stage)
+    for r, o in zip(ref, ora):
+        assert np.array_equal(r.view(np.uint32), o.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("stage", ["ofdm", "gain", "guard"])
+def test_float_stages(rng, mode, stage):
+    bits = bits_for(rng, mode, 2)
+    ref = refwrap.RefChain(mode=mode, stop_after=stage).run(bits)
+    ora = oracle.OracleChain(mode=mode).run(bits, stage=stage)
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < FFT_TOL
+
+
+@pytest.mark.parametrize("gain_mode,dg,norm,var", [("fix", 1.0, 1.0, 4.0), ("max", 0.8, 1.0, 4.0),
+                                                    ("var", 0.7, 1.0 / 46000.0, 3.0)])
+def test_gain_modes(rng, gain_mode, dg, norm, var):
+    bits = bits_for(rng, 2, 2)
+    kw = dict(mode=2, gain_mode=gain_mode, digital_gain=dg, normalise=norm, gain_variance=var)
+    ref = refwrap.RefChain(**kw).run(bits)
+    ora = oracle.OracleChain(**kw).run(bits)
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < FFT_TOL
+
+
+@pytest.mark.parametrize("mode,W", [(1, 10), (2, 7), (3, 4), (4, 32)])
+def test_ofdm_windowing(rng, mode, W):
+    bits = bits_for(rng, mode, 2)
+    ref = refwrap.RefChain(mode=mode, window_overlap=W).run(bits)
+    ora = oracle.OracleChain(mode=mode, window_overlap=W).run(bits)
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < FFT_TOL
+
+
+@pytest.mark.parametrize("mode,comb,pattern,old", [(1, 1, 11, 0), (1, 23, 69, 1), (2, 4, 0, 0), (2, 23, 35, 1)])
+def test_tii(rng, mode, comb, pattern, old):
+    bits = bits_for(rng, mode, 4)
+    tii = (comb, pattern, old)
+    ref = refwrap.RefChain(mode=mode, tii=tii, stop_after="mux").run(bits)
+    ora = oracle.OracleChain(mode=mode, tii=tii).run(bits, stage="mux")
+    K = oracle.mode_params(mode).K
+    for i, (r, o) in enumerate(zip(ref, ora)):
+        assert np.array_equal(r.view(np.uint32), o.view(np.uint32))
+        # inserted on every second TF starting with the first (TII.cpp:225-242)
+        assert (np.count_nonzero(r[:K]) > 0) == (i % 2 == 0)
+    # full chain: the null symbol borrows symbol 1's gain (GainControl.cpp:139-144)
+    ref = refwrap.RefChain(mode=mode, tii=tii).run(bits)
+    ora = oracle.OracleChain(mode=mode, tii=tii).run(bits)
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < FFT_TOL
+
+
+def test_tii_rejected_modes():
+    for mode in (3, 4):
+        rc, _ = oracle.tii_carriers(mode, 1, 1)
+        assert rc != 0
+
+
+@pytest.mark.parametrize("clip,errclip", [(50.0, 0.1), (70.0, 0.02)])
+def test_cfr(rng, clip, errclip):
+    bits = bits_for(rng, 1, 2)
+    ref = refwrap.RefChain(mode=1, cfr=(clip, errclip), stop_after="ofdm").run(bits)
+    ora = oracle.OracleChain(mode=1, cfr=(clip, errclip)).run(bits, stage="ofdm")
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < 2e-6
+
+
+@pytest.mark.parametrize("clock,rate", [(32768000, 2048000), (400000000, 2048000), (100000000, 2048000)])
+def test_cic_equalizer(rng, clock, rate):
+    bits = bits_for(rng, 1, 1)
+    ref = refwrap.RefChain(mode=1, clock_rate=clock, output_rate=rate, stop_after="ciceq").run(bits)
+    ora = oracle.OracleChain(mode=1, clock_rate=clock, output_rate=rate).run(bits, stage="ciceq")
+    assert rel_rms(ora[0], ref[0]) < 1e-6
+
+
+def test_fir_default_and_file(rng, tmp_path):
+    bits = bits_for(rng, 1, 2)
+    ref = refwrap.RefChain(mode=1, fir_taps_file="default").run(bits)
+    ora = oracle.OracleChain(mode=1, fir_taps=oracle.fir_default_taps()).run(bits)
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < FFT_TOL
+    taps = rng.standard_normal(12).astype(np.float32) / 4
+    path = str(tmp_path / "taps.txt")
+    write_taps_file(path, taps)
+    ref = refwrap.RefChain(mode=3, fir_taps_file=path).run(bits_for(rng, 3, 1))
+    # re-read what the reference parsed: text round trip of float32 is exact with %.9g
+    bits3 = bits_for(rng, 3, 1)
+    ref = refwrap.RefChain(mode=3, fir_taps_file=path).run(bits3)
+    ora = oracle.OracleChain(mode=3, fir_taps=taps).run(bits3)
+    assert rel_rms(ora[0], ref[0]) < FFT_TOL
+
+
+@pytest.mark.parametrize("mode,rate", [(1, 8192000), (1, 10000000), (2, 4096000), (1, 1536000), (4, 2500000)])
+def test_resampler_with_state(rng, mode, rate):
+    bits = bits_for(rng, mode, 3)
+    ref = refwrap.RefChain(mode=mode, output_rate=rate, fir_taps_file="default").run(bits)
+    ora = oracle.OracleChain(mode=mode, output_rate=rate, fir_taps=oracle.fir_default_taps()).run(bits)
+    for r, o in zip(ref, ora):
+        assert r.size == o.size
+        assert rel_rms(o, r) < FFT_TOL
+
+
+def test_memless_poly_and_lut(rng, tmp_path):
+    bits = bits_for(rng, 2, 2)
+    am = [1.0, 0.12, -0.3, 0.05, 0.01]
+    pm = [0.02, -0.4, 0.3, 0.1, -0.05]
+    p = str(tmp_path / "poly.coef")
+    write_poly_file(p, am, pm)
+    kw = dict(mode=2, normalise=1.0 / 46000.0)
+    ref = refwrap.RefChain(poly_coef_file=p, poly_threads=1, **kw).run(bits)
+    ora = oracle.OracleChain(poly=am + pm, **kw).run(bits)
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < FFT_TOL
+    lut = 1.0 + 0.1 * rng.standard_normal(32).astype(np.float32)
+    scale = np.float32(2 ** 32 / 1.5)
+    p2 = str(tmp_path / "lut.coef")
+    write_lut_file(p2, scale, lut)
+    ref = refwrap.RefChain(poly_coef_file=p2, poly_threads=1, **kw).run(bits)
+    ora = oracle.OracleChain(lut=(scale, lut), **kw).run(bits)
+    for r, o in zip(ref, ora):
+        # a sample whose magnitude lands within float rounding of a bin edge may
+        # pick the neighbouring LUT entry; allow a handful
+        bad = np.abs(o - r) > 1e-5 * np.abs(r).max()
+        assert bad.sum() <= 4
+
+
+@pytest.mark.parametrize("fmt,dg", [("s16", 0.8), ("s16", 3.0), ("u8", 0.003), ("s8", 0.003), ("s8", 0.02)])
+def test_format_converter(rng, fmt, dg):
+    bits = bits_for(rng, 2, 1)
+    dt = {"s16": np.int16, "u8": np.uint8, "s8": np.int8}[fmt]
+    ref = refwrap.RefChain(mode=2, digital_gain=dg, fmt=fmt).run(bits, dtype=dt)
+    ora = oracle.OracleChain(mode=2, digital_gain=dg, fmt=fmt).run(bits)
+    r, o = ref[0].astype(np.int32), ora[0].astype(np.int32)
+    assert r.size == o.size
+    # float32 inputs differ by ~1e-7 relative, so a value sitting on an integer
+    # boundary may truncate to the neighbouring integer
+    assert np.abs(r - o).max() <= 1
+    assert np.count_nonzero(r != o) < 0.002 * r.size
+
+
+def test_full_chain_c3(rng, tmp_path):
+    """BASELINE config 3: FIR + resampler to 8.192 Msps + MemlessPoly, normalised."""
+    bits = bits_for(rng, 1, 2)
+    am = [1.0, 0.05, -0.02, 0.0, 0.0]
+    pm = [0.0, 0.1, -0.05, 0.0, 0.0]
+    p = str(tmp_path / "poly.coef")
+    write_poly_file(p, am, pm)
+    kw = dict(mode=1, output_rate=8192000, normalise=1.0 / 46000.0)
+    ref = refwrap.RefChain(fir_taps_file="default", poly_coef_file=p, poly_threads=1, **kw).run(bits)
+    ora = oracle.OracleChain(fir_taps=oracle.fir_default_taps(), poly=am + pm, **kw).run(bits)
+    for r, o in zip(ref, ora):
+        assert rel_rms(o, r) < FFT_TOL
