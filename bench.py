@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the COFDM I/Q hot path (BASELINE.json metric: ETI frames/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): TM I, 1024 transmission frames (= 4096 ETI
+frames) per step and per GPU, native 2.048 Msps, FIRFilter with the default
+taps, complexf output.  One step = one pass of the whole kernel family over
+that batch.  Synthetic input: uniform random bytes of the BlockPartitioner
+block size (every bit pattern is a valid QPSK input).
+
+  value  device-resident ETI frames/s (inputs and outputs in HBM), CUDA events
+  e2e    the same through dabmod_b200_process_batch with pinned HOST buffers
+         (H2D of the bits and D2H of the I/Q inside the timed region)
+
+N > 1: one process per GPU (torchrun), frame-sharded weak scaling, no data-path
+collective; time = max over ranks of the device time.
+
+--impl reference: the reference's own CPU code (oracle/_ref/libdabmod_ref.so =
+unmodified ODR-DabMod blocks, FFTW replaced by its vendored float KISS FFT),
+one independent modulator per host core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODE = 1
+TFS_PER_STEP = 1024
+ETI_PER_TF = 4
+TF_IN_BYTES = 28800
+TF_SAMPLES = 196608
+# algorithmic bytes per TM I TF
+SYM_BYTES_PER_TF = TF_IN_BYTES + TF_SAMPLES * 8          # 1 601 664
+FIR_BYTES_PER_TF = 2 * TF_SAMPLES * 8                    # 3 145 728
+METRIC = "ETI frames/sec (TM I, 2.048 Msps I/Q) at 1/2/4/8 B200 vs reference CPU"
+WORKLOAD = "TM I, batched 1024 frames on 1xB200, native rate, FIRFilter enabled (default taps)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]      # the idle->busy ramp lands in the lower half
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference / CPU baseline
+# ---------------------------------------------------------------------------
+def cpu_chain_factory():
+    """Returns (kind, make_chain, latency) for the CPU implementation of the path."""
+    from oracle import refwrap
+    if refwrap.available():
+        def mk():
+            return refwrap.RefChain(mode=MODE, fir_taps_file="default")
+        return "reference", mk
+    from oracle import oracle
+
+    def mk2():
+        return oracle.OracleChain(mode=MODE, fir_taps=oracle.fir_default_taps())
+    return "port", mk2
+
+
+def run_cpu(n_threads, tfs_per_thread, seed=99):
+    """n_threads independent modulators (one per host core), each fed tfs_per_thread TFs.
+    Returns (eti_frames_per_s, seconds, kind)."""
+    kind, mk = cpu_chain_factory()
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 256, (8, TF_IN_BYTES), dtype=np.uint8)
+    chains = [mk() for _ in range(n_threads)]
+    feed = (lambda c, b: c.feed_raw(b)) if kind == "reference" else (lambda c, b: c.process(b))
+    # prime the pipelined stages (reference: 2 calls of latency) outside the timed region
+    for c in chains:
+        for i in range(3):
+            feed(c, bits[i % 8])
+    barrier = threading.Barrier(n_threads + 1)
+
+    def work(c):
+        barrier.wait()
+        for i in range(tfs_per_thread):
+            feed(c, bits[i % 8])
+        barrier.wait()
+
+    ths = [threading.Thread(target=work, args=(c,)) for c in chains]
+    for t in ths:
+        t.start()
+    barrier.wait()
+    t0 = time.perf_counter()
+    barrier.wait()
+    dt = time.perf_counter() - t0
+    for t in ths:
+        t.join()
+    for c in chains:
+        c.close()
+    return n_threads * tfs_per_thread * ETI_PER_TF / dt, dt, kind
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    tfs = 24                                   # per thread per step: ~0.1-0.2 s of CPU work
+    for _ in range(args.warmup):
+        run_cpu(cores, tfs)
+    t_total, frames = 0.0, 0
+    kind = "reference"
+    for _ in range(args.steps):
+        v, dt, kind = run_cpu(cores, tfs)
+        t_total += dt
+        frames += cores * tfs * ETI_PER_TF
+    value = frames / t_total
+    sample = "%d TFs per thread per step x %d threads (one independent modulator per host core)" % (tfs, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "ETI frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mode": MODE, "tfs_per_step": cores * tfs,
+                   "note": "CPU arm: bounded sample of the same workload"},
+        "cpu_baseline": {"value": value, "unit": "ETI frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "ETI frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import dabmod_loader
+
+    dm = dabmod_loader.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_tf = TFS_PER_STEP
+    mod = dm.Modulator(mode=MODE, fir_taps="default", max_batch=n_tf, device=local_rank)
+    out_bytes = n_tf * mod.tf_out_bytes
+    in_bytes = n_tf * mod.tf_in_bytes
+
+    # synthetic input, distinct per rank; 4 rotating device copies
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    host_bits = torch.randint(0, 256, (n_tf, mod.tf_in_bytes), dtype=torch.uint8, generator=g).pin_memory()
+    d_bits = [host_bits.to("cuda", non_blocking=True).clone() for _ in range(4)]
+    d_out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+    host_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_device(i):
+        mod.process_batch_device(d_bits[i % 4].data_ptr(), n_tf, d_out.data_ptr(), stream.cuda_stream)
+
+    def step_e2e():
+        return mod.process_batch_ptr(host_bits.data_ptr(), n_tf, host_out.data_ptr(), out_bytes)
+
+    # ---- device-resident: `value` ----
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    barrier()
+    launches = mod.last_launch_count * args.steps
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+
+    # ---- per-kernel timing for the roofline (same workload, events around each kernel) ----
+    mod.set_param("profile", 1)
+    ktimes = {}
+    reps = max(3, min(args.steps, 10))
+    for i in range(reps):
+        step_device(i)
+        torch.cuda.synchronize()
+        for name, t in mod.kernel_times():
+            ktimes.setdefault(name, []).append(t)
+    mod.set_param("profile", 0)
+    kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
+
+    # ---- end to end through the host-buffer C ABI: `e2e` ----
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_s = float(dt.item())
+    clocks = sampler.stop() if rank == 0 else None
+    checksum = int(host_out[:4096].to(torch.int64).sum().item())  # the D2H result is read
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    eti_per_step = world * n_tf * ETI_PER_TF
+    value = eti_per_step * args.steps / (ms_total * 1e-3)
+    e2e_value = eti_per_step * e2e_steps / e2e_s
+
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = {"k_symbols": SYM_BYTES_PER_TF * n_tf, "k_fir": FIR_BYTES_PER_TF * n_tf}
+    dom = max(kavg, key=lambda k: kavg[k])
+    achieved = bytes_per_launch[dom] / (kavg[dom] * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": bytes_per_launch[dom], "kernel_ms": kavg[dom],
+        "all_kernels": {k: {"ms": kavg[k], "GB/s": bytes_per_launch[k] / (kavg[k] * 1e-3) / 1e9,
+                            "frac": bytes_per_launch[k] / (kavg[k] * 1e-3) / 1e9 / peak} for k in kavg},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            roofline["traffic"] = json.load(f).get(dom)
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        tfs = 96
+        v, dt_cpu, kind = run_cpu(cores, tfs)
+        cpu = {"value": v, "unit": "ETI frames/s", "cores": cores, "kind": kind,
+               "sample": "%d TFs per thread x %d threads, %.1f s (same TM I + FIR default taps chain)" % (tfs, cores, dt_cpu)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "ETI frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mode": MODE, "tfs_per_step_per_gpu": n_tf,
+                   "eti_frames_per_step": eti_per_step, "output": "complexf", "gain": "var",
+                   "l2": "per-step working set 3.2 GB (1.6 GB symbol-stage + 1.6 GB output) >> 126 MB L2; "
+                         "input bits rotate over 4 buffers",
+                   "parallelism": "frame-sharded x%d, no collective" % world},
+        "e2e": {"value": e2e_value, "unit": "ETI frames/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "checksum": checksum},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

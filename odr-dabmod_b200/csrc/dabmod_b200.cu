@@ -1,0 +1,783 @@
+// C ABI (include/dabmod_b200.h) over the sm_100a kernel family.
+// Host orchestration only: tables, buffers, streams, launches, parameters.
+#include "../../include/dabmod_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "tables.h"
+
+using namespace dabmod;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct ApiError : std::runtime_error {
+    int code;
+    ApiError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            throw ApiError(DABMOD_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count)
+    {
+        release();
+        if (count == 0) return;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess)
+            throw ApiError(DABMOD_B200_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        n = count;
+    }
+    void upload(const std::vector<T> &v, cudaStream_t s)
+    {
+        if (v.size() > n) alloc(v.size());
+        if (!v.empty())
+            CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+size_t format_bytes(int fmt)
+{
+    switch (fmt) {
+        case DABMOD_B200_FMT_COMPLEXF: return 8;
+        case DABMOD_B200_FMT_S16: return 4;
+        case DABMOD_B200_FMT_U8:
+        case DABMOD_B200_FMT_S8: return 2;
+        default: throw ApiError(DABMOD_B200_EINVAL, "FormatConverter: Invalid format");
+    }
+}
+
+} // namespace
+
+struct dabmod_b200 {
+    dabmod_b200_config cfg{};
+    ModeInfo m{};
+    std::mutex mtx;                // guards parameters against set_param from RC threads
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+
+    // parameters (host copies)
+    std::vector<float> fir_taps;
+    int dpd_mode = 0;
+    float dpd[33] = {0};
+    bool use_cic = false;
+    bool tii_supported = false;
+    uint64_t tf_counter = 0;       // TFs processed since create/reset (TII parity)
+    bool tables_dirty = true;
+
+    // device tables
+    DevBuf<uint16_t> d_bin_of_src;
+    DevBuf<uint8_t> d_phase0;
+    DevBuf<float> d_cic;
+    DevBuf<float> d_twiddle;       // interleaved re/im, 2048 entries
+    DevBuf<uint16_t> d_tii_bin;
+    DevBuf<float> d_tii_val;
+    DevBuf<float> d_window;
+    DevBuf<float> d_lut;
+    DevBuf<unsigned long long> d_clipped;
+    int tii_count = 0;
+
+    // work buffers for max_batch TFs
+    DevBuf<uint8_t> d_bits;
+    DevBuf<unsigned char> d_out;
+    DevBuf<float2> d_tmp;          // symbol-stage output when another kernel follows
+
+    uint64_t clipped_last = 0;
+    uint32_t launches_last = 0;
+
+    // optional per-kernel timing
+    bool profile = false;
+    struct Timed { const char *name; cudaEvent_t a, b; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    cudaEvent_t next_event()
+    {
+        if (events_used == event_pool.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) throw std::runtime_error("cudaEventCreate failed");
+            event_pool.push_back(e);
+        }
+        return event_pool[events_used++];
+    }
+
+    size_t out_samples_per_tf() const { return (size_t)m.tf_samples; }
+    size_t out_bytes_per_tf() const { return out_samples_per_tf() * format_bytes(cfg.format); }
+    bool has_fir() const { return !fir_taps.empty(); }
+    bool has_post() const { return dpd_mode != 0 || cfg.format != DABMOD_B200_FMT_COMPLEXF; }
+};
+
+namespace {
+
+void build_tables(dabmod_b200 *h)
+{
+    const ModeInfo &m = h->m;
+    const dabmod_b200_config &c = h->cfg;
+    cudaStream_t s = h->s_compute;
+
+    const std::vector<int> dest = interleaver_dest(m);
+    const std::vector<uint8_t> q = phase_ref_quarter_turns(m);
+    std::vector<uint16_t> bin(m.K);
+    std::vector<uint8_t> ph0(m.K);
+    for (int j = 0; j < m.K; j++) {
+        bin[j] = (uint16_t)bin_of_carrier(m, dest[j]);
+        ph0[j] = (uint8_t)(2 * q[dest[j]]);
+    }
+    h->d_bin_of_src.upload(bin, s);
+    h->d_phase0.upload(ph0, s);
+
+    unsigned ratio = 1;
+    const uint64_t rate = c.output_rate ? c.output_rate : 2048000;
+    h->use_cic = cic_enabled(c.clock_rate, rate, ratio);
+    std::vector<float> cic_pos;
+    if (h->use_cic) {
+        cic_pos = cic_filter(m.K, (float)m.N * (float)rate / 2048000.0f, (int)ratio);
+        std::vector<float> cic_src(m.K);
+        for (int j = 0; j < m.K; j++) cic_src[j] = cic_pos[dest[j]];
+        h->d_cic.upload(cic_src, s);
+    }
+
+    // TII symbol (TII.cpp:172-211): carrier pair (ix, ix+1) = phaseref[ix] twice,
+    // or phaseref[ix], phaseref[ix+1] for the old variant.
+    std::vector<int> pairs;
+    h->tii_supported = tii_pairs(m, c.tii_comb, c.tii_pattern, pairs);
+    std::vector<uint16_t> tbin;
+    std::vector<float> tval;
+    if (h->tii_supported && c.tii_enable) {
+        static const float qre[4] = {1, 0, -1, 0}, qim[4] = {0, 1, 0, -1};
+        for (int ix : pairs) {
+            for (int o = 0; o < 2; o++) {
+                const int src = (o == 1 && c.tii_old_variant) ? ix + 1 : ix;
+                float g = h->use_cic ? cic_pos[ix + o] : 1.0f;
+                tbin.push_back((uint16_t)bin_of_carrier(m, ix + o));
+                tval.push_back(qre[q[src]] * g);
+                tval.push_back(qim[q[src]] * g);
+            }
+        }
+    }
+    h->tii_count = (int)tbin.size();
+    if (h->tii_count > MAX_TII * 2) throw ApiError(DABMOD_B200_EINVAL, "too many TII carriers");
+    h->d_tii_bin.upload(tbin, s);
+    h->d_tii_val.upload(tval, s);
+
+    if (c.window_overlap > 0) h->d_window.upload(guard_window(c.window_overlap), s);
+
+    if (h->dpd_mode == DABMOD_B200_DPD_LUT) {
+        std::vector<float> lut(h->dpd + 1, h->dpd + 33);
+        h->d_lut.upload(lut, s);
+    }
+    h->tables_dirty = false;
+}
+
+PostParams make_post(dabmod_b200 *h, bool enabled)
+{
+    PostParams pp{};
+    if (!enabled) return pp;
+    pp.dpd_mode = h->dpd_mode;
+    pp.format = h->cfg.format;
+    if (h->dpd_mode == DABMOD_B200_DPD_ODD_POLY) {
+        for (int i = 0; i < 5; i++) { pp.am[i] = h->dpd[i]; pp.pm[i] = h->dpd[5 + i]; }
+    }
+    else if (h->dpd_mode == DABMOD_B200_DPD_LUT) {
+        pp.lut_scale = h->dpd[0];
+        pp.lut = h->d_lut.p;
+    }
+    pp.clipped = h->d_clipped.p;
+    return pp;
+}
+
+template <int N>
+void launch_symbols_n(const SymParams &p, bool post, int grid, cudaStream_t s)
+{
+    const size_t smem = sizeof(SymSmem);
+    if (post) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_symbols<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_symbols<N, true><<<grid, SYM_THREADS, smem, s>>>(p);
+    }
+    else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_symbols<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_symbols<N, false><<<grid, SYM_THREADS, smem, s>>>(p);
+    }
+}
+
+template <bool POST>
+void launch_fir_p(const FirParams &p, int ntaps, int grid, cudaStream_t s)
+{
+    if (ntaps <= 16) k_fir<16, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+    else if (ntaps <= 32) k_fir<32, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+    else if (ntaps <= 48) k_fir<48, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+    else if (ntaps <= 64) k_fir<64, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+    else if (ntaps <= 96) k_fir<96, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+    else k_fir<128, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+}
+
+struct ProfScope {
+    dabmod_b200 *h;
+    cudaStream_t s;
+    size_t slot = 0;
+    bool on;
+    ProfScope(dabmod_b200 *h_, const char *name, cudaStream_t s_) : h(h_), s(s_), on(h_->profile)
+    {
+        if (!on) return;
+        dabmod_b200::Timed t{name, h->next_event(), h->next_event()};
+        cudaEventRecord(t.a, s);
+        slot = h->timed.size();
+        h->timed.push_back(t);
+    }
+    void end()
+    {
+        if (on) cudaEventRecord(h->timed[slot].b, s);
+    }
+};
+
+// Enqueue the kernel family for n_tf TFs: d_bits -> d_out.  `tf0` = index of
+// the first TF within the handle's work buffers (for the temp buffer offset).
+void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, size_t tmp_tf0,
+             uint64_t stream_tf, cudaStream_t s, uint32_t &launches)
+{
+    const ModeInfo &m = h->m;
+    const dabmod_b200_config &c = h->cfg;
+    const bool fir = h->has_fir();
+    const bool post = h->has_post();
+
+    SymParams sp{};
+    sp.L = m.L; sp.K = m.K; sp.N = m.N;
+    sp.null_size = m.null_size; sp.sym_size = m.sym_size;
+    sp.tf_in_bytes = m.tf_in_bytes; sp.tf_samples = m.tf_samples;
+    sp.G = SYM_POINTS / m.N;
+    sp.n_groups = (m.L + 1 + sp.G - 1) / sp.G;
+    // chunking: enough CTAs to fill the machine several times over, but chunks
+    // long enough to amortise the per-CTA tables and the phase prefix
+    {
+        const int target_ctas = h->sm_count * 6 * 4;
+        int chunks = (int)std::min<size_t>((size_t)sp.n_groups / 2, std::max<size_t>(1, (target_ctas + n_tf - 1) / n_tf));
+        chunks = std::max(1, std::min(chunks, 11));
+        sp.groups_per_chunk = (sp.n_groups + chunks - 1) / chunks;
+        if (sp.groups_per_chunk < 2) sp.groups_per_chunk = 2;
+        sp.n_chunks = (sp.n_groups + sp.groups_per_chunk - 1) / sp.groups_per_chunk;
+    }
+    sp.bin_of_src = h->d_bin_of_src.p;
+    sp.phase0 = h->d_phase0.p;
+    sp.cic = h->use_cic ? h->d_cic.p : nullptr;
+    sp.twiddle = reinterpret_cast<const float2 *>(h->d_twiddle.p);
+    sp.tii_count = h->tii_count;
+    sp.tii_parity = 0;
+    sp.tii_bin = h->d_tii_bin.p;
+    sp.tii_val = reinterpret_cast<const float2 *>(h->d_tii_val.p);
+    sp.cfr = c.cfr_enable;
+    sp.cfr_clip = c.cfr_clip;
+    sp.cfr_errclip = c.cfr_errclip;
+    sp.gain_mode = c.gain_mode;
+    sp.gain_const = c.normalise * c.digital_gain;
+    sp.var_factor = c.gain_variance;
+    sp.window = c.window_overlap;
+    sp.window_tab = h->d_window.p;
+    sp.bits = d_bits;
+    sp.tf_offset = stream_tf;
+    const bool sym_last = !fir;
+    sp.out = sym_last ? d_out : (void *)(h->d_tmp.p + tmp_tf0 * (size_t)m.tf_samples);
+    sp.post = make_post(h, sym_last && post);
+
+    const int grid = (int)(n_tf * sp.n_chunks);
+    const bool sym_post = sym_last && post;
+    ProfScope prof_sym(h, "k_symbols", s);
+    switch (m.N) {
+        case 2048: launch_symbols_n<2048>(sp, sym_post, grid, s); break;
+        case 1024: launch_symbols_n<1024>(sp, sym_post, grid, s); break;
+        case 512: launch_symbols_n<512>(sp, sym_post, grid, s); break;
+        default: launch_symbols_n<256>(sp, sym_post, grid, s); break;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    prof_sym.end();
+    launches++;
+
+    if (fir) {
+        FirParams fp{};
+        fp.in = reinterpret_cast<const float2 *>(sp.out);
+        fp.out = d_out;
+        fp.tf_samples = m.tf_samples;
+        fp.tiles_per_tf = (m.tf_samples + FIR_TILE - 1) / FIR_TILE;
+        std::memset(fp.taps, 0, sizeof(fp.taps));
+        std::memcpy(fp.taps, h->fir_taps.data(), h->fir_taps.size() * sizeof(float));
+        fp.post = make_post(h, post);
+        const int fgrid = (int)(n_tf * fp.tiles_per_tf);
+        ProfScope prof_fir(h, "k_fir", s);
+        if (post) launch_fir_p<true>(fp, (int)h->fir_taps.size(), fgrid, s);
+        else launch_fir_p<false>(fp, (int)h->fir_taps.size(), fgrid, s);
+        CUDA_CHECK(cudaGetLastError());
+        prof_fir.end();
+        launches++;
+    }
+}
+
+void validate_config(const dabmod_b200_config &c)
+{
+    if (c.abi_version != DABMOD_B200_ABI_VERSION)
+        throw ApiError(DABMOD_B200_EINVAL, "dabmod_b200_config.abi_version mismatch");
+    if (c.mode < 0 || c.mode > 4) throw ApiError(DABMOD_B200_EINVAL, "DabModulator::setMode invalid mode size");
+    if (c.gain_mode < 0 || c.gain_mode > 2) throw ApiError(DABMOD_B200_EINVAL, "Internal error: invalid gainmode");
+    if (c.fir_ntaps < 0 || (c.fir_ntaps > 0 && !c.fir_taps)) throw ApiError(DABMOD_B200_EINVAL, "FIRFilter: taps missing");
+    if (c.fir_ntaps > MAX_FIR_TAPS)
+        throw ApiError(DABMOD_B200_EUNSUPPORTED, "FIRFilter: more than 128 taps are not supported");
+    if (c.dpd_mode < 0 || c.dpd_mode > 2 || (c.dpd_mode && !c.dpd_coefs))
+        throw ApiError(DABMOD_B200_EINVAL, "MemlessPoly: invalid coefficients");
+    format_bytes(c.format);
+    if (c.window_overlap < 0) throw ApiError(DABMOD_B200_EINVAL, "windowlen must be >= 0");
+    if (c.window_overlap > 0)
+        throw ApiError(DABMOD_B200_EUNSUPPORTED, "OFDM windowing is not implemented yet");
+    if (c.cfr_enable) throw ApiError(DABMOD_B200_EUNSUPPORTED, "CFR is not implemented yet");
+    if (c.output_rate && c.output_rate != 2048000)
+        throw ApiError(DABMOD_B200_EUNSUPPORTED, "Resampler is not implemented yet");
+    if (c.max_batch < 0) throw ApiError(DABMOD_B200_EINVAL, "max_batch < 0");
+}
+
+int guard(const std::function<void()> &fn)
+{
+    try {
+        fn();
+        return DABMOD_B200_OK;
+    }
+    catch (const ApiError &e) {
+        g_last_error = e.what();
+        return e.code;
+    }
+    catch (const std::bad_alloc &) {
+        g_last_error = "out of host memory";
+        return DABMOD_B200_ENOMEM;
+    }
+    catch (const std::exception &e) {
+        g_last_error = e.what();
+        return DABMOD_B200_EINVAL;
+    }
+}
+} // namespace
+
+extern "C" {
+
+const char *dabmod_b200_last_error(void) { return g_last_error.c_str(); }
+
+void dabmod_b200_config_init(dabmod_b200_config *cfg)
+{
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = DABMOD_B200_ABI_VERSION;
+    cfg->mode = 1;
+    cfg->gain_mode = DABMOD_B200_GAIN_VAR;
+    cfg->output_rate = 2048000;
+    cfg->digital_gain = 1.0f;
+    cfg->normalise = 1.0f;
+    cfg->gain_variance = 4.0f;
+    cfg->cfr_clip = 1.0f;
+    cfg->cfr_errclip = 1.0f;
+    cfg->max_batch = 1;
+}
+
+int dabmod_b200_default_fir_taps(float *taps, int cap)
+{
+    const std::vector<float> t = default_fir_taps();
+    if (taps) std::memcpy(taps, t.data(), sizeof(float) * std::min<size_t>(t.size(), cap > 0 ? cap : 0));
+    return (int)t.size();
+}
+
+int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
+{
+    if (out) *out = nullptr;
+    dabmod_b200 *h = nullptr;
+    int rc = guard([&] {
+        if (!cfg || !out) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        validate_config(*cfg);
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw ApiError(DABMOD_B200_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                                  " (this library has no CPU fallback)");
+        if (cfg->device < 0 || cfg->device >= ndev) throw ApiError(DABMOD_B200_EINVAL, "invalid device ordinal");
+        CUDA_CHECK(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop{};
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major != 10)
+            throw ApiError(DABMOD_B200_ECUDA, "device is not compute capability 10.x (built for sm_100a only)");
+
+        h = new dabmod_b200();
+        h->cfg = *cfg;
+        if (h->cfg.mode == 0) h->cfg.mode = 1;
+        if (h->cfg.output_rate == 0) h->cfg.output_rate = 2048000;
+        if (h->cfg.max_batch <= 0) h->cfg.max_batch = 1;
+        h->device = cfg->device;
+        h->sm_count = prop.multiProcessorCount;
+        h->m = mode_info(h->cfg.mode);
+        if (cfg->fir_ntaps > 0) h->fir_taps.assign(cfg->fir_taps, cfg->fir_taps + cfg->fir_ntaps);
+        h->cfg.fir_taps = nullptr;
+        h->dpd_mode = cfg->dpd_mode;
+        if (cfg->dpd_mode == DABMOD_B200_DPD_ODD_POLY) std::memcpy(h->dpd, cfg->dpd_coefs, 10 * sizeof(float));
+        if (cfg->dpd_mode == DABMOD_B200_DPD_LUT) std::memcpy(h->dpd, cfg->dpd_coefs, 33 * sizeof(float));
+        h->cfg.dpd_coefs = nullptr;
+
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+
+        std::vector<float> tw;
+        twiddle_table(SYM_POINTS, tw);
+        h->d_twiddle.upload(tw, h->s_compute);
+        h->d_clipped.alloc(1);
+        CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
+        build_tables(h);
+
+        const size_t nb = (size_t)h->cfg.max_batch;
+        h->d_bits.alloc(nb * h->m.tf_in_bytes);
+        h->d_out.alloc(nb * h->out_bytes_per_tf());
+        h->d_tmp.alloc(nb * (size_t)h->m.tf_samples);
+        CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+        *out = h;
+    });
+    if (rc != DABMOD_B200_OK && h) {
+        dabmod_b200_destroy(h);
+    }
+    return rc;
+}
+
+void dabmod_b200_destroy(dabmod_b200 *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->s_compute) cudaStreamSynchronize(h->s_compute);
+    if (h->s_in) cudaStreamSynchronize(h->s_in);
+    if (h->s_out) cudaStreamSynchronize(h->s_out);
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    for (auto e : h->ev_in) cudaEventDestroy(e);
+    for (auto e : h->ev_done) cudaEventDestroy(e);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    delete h;
+}
+
+size_t dabmod_b200_tf_in_bytes(const dabmod_b200 *h) { return h ? (size_t)h->m.tf_in_bytes : 0; }
+size_t dabmod_b200_tf_out_bytes(const dabmod_b200 *h) { return h ? h->out_bytes_per_tf() : 0; }
+size_t dabmod_b200_tf_out_samples(const dabmod_b200 *h) { return h ? h->out_samples_per_tf() : 0; }
+
+int dabmod_b200_process_batch_device(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_iq_out,
+                                     void *stream)
+{
+    return guard([&] {
+        if (!h || (n_tf && (!d_bits || !d_iq_out))) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        if (n_tf > (size_t)h->cfg.max_batch)
+            throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
+        std::lock_guard<std::mutex> lock(h->mtx);
+        CUDA_CHECK(cudaSetDevice(h->device));
+        cudaStream_t s = stream ? (cudaStream_t)stream : h->s_compute;
+        if (h->tables_dirty) {
+            build_tables(h);
+            if (s != h->s_compute) CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+        }
+        h->launches_last = 0;
+        h->timed.clear();
+        h->events_used = 0;
+        if (n_tf == 0) return;
+        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
+            CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), s));
+        enqueue(h, d_bits, n_tf, d_iq_out, 0, h->tf_counter, s, h->launches_last);
+        h->tf_counter += n_tf;
+    });
+}
+
+int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, void *iq_out, size_t cap,
+                              size_t *out_bytes)
+{
+    if (out_bytes) *out_bytes = 0;
+    return guard([&] {
+        if (!h || (n_tf && (!bits || !iq_out))) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        if (n_tf > (size_t)h->cfg.max_batch)
+            throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
+        const size_t in_tf = h->m.tf_in_bytes, out_tf = h->out_bytes_per_tf();
+        if (cap < n_tf * out_tf) throw ApiError(DABMOD_B200_EINVAL, "output buffer too small");
+        std::lock_guard<std::mutex> lock(h->mtx);
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (h->tables_dirty) build_tables(h);
+        h->launches_last = 0;
+        h->timed.clear();
+        h->events_used = 0;
+        if (n_tf == 0) return;
+        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
+            CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
+
+        // Software pipeline over slices of the batch: H2D(i+1) | kernels(i) | D2H(i-1)
+        // on three streams, so PCIe traffic in both directions hides the compute.
+        const size_t slice = std::max<size_t>(1, std::min<size_t>(n_tf, (48u << 20) / out_tf));
+        const size_t n_slices = (n_tf + slice - 1) / slice;
+        while (h->ev_in.size() < n_slices) {
+            cudaEvent_t a, b;
+            CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            h->ev_in.push_back(a);
+            h->ev_done.push_back(b);
+        }
+        for (size_t i = 0; i < n_slices; i++) {
+            const size_t t0 = i * slice, nt = std::min(slice, n_tf - t0);
+            CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p + t0 * in_tf, bits + t0 * in_tf, nt * in_tf,
+                                       cudaMemcpyHostToDevice, h->s_in));
+            CUDA_CHECK(cudaEventRecord(h->ev_in[i], h->s_in));
+            CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_in[i], 0));
+            enqueue(h, h->d_bits.p + t0 * in_tf, nt, h->d_out.p + t0 * out_tf, t0, h->tf_counter + t0,
+                    h->s_compute, h->launches_last);
+            CUDA_CHECK(cudaEventRecord(h->ev_done[i], h->s_compute));
+            CUDA_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[i], 0));
+            CUDA_CHECK(cudaMemcpyAsync((unsigned char *)iq_out + t0 * out_tf, h->d_out.p + t0 * out_tf,
+                                       nt * out_tf, cudaMemcpyDeviceToHost, h->s_out));
+        }
+        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF) {
+            CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+            unsigned long long v = 0;
+            CUDA_CHECK(cudaMemcpy(&v, h->d_clipped.p, sizeof(v), cudaMemcpyDeviceToHost));
+            h->clipped_last = v;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(h->s_out));
+        h->tf_counter += n_tf;
+        if (out_bytes) *out_bytes = n_tf * out_tf;
+    });
+}
+
+int dabmod_b200_process(dabmod_b200 *h, const uint8_t *bits, size_t nbytes, void *iq_out, size_t cap,
+                        size_t *out_bytes)
+{
+    if (out_bytes) *out_bytes = 0;
+    if (h && nbytes != (size_t)h->m.tf_in_bytes) {
+        g_last_error = "QpskSymbolMapper::process input size not valid: " + std::to_string(nbytes) +
+                       " != " + std::to_string(h->m.tf_in_bytes);
+        return DABMOD_B200_EINVAL;
+    }
+    return dabmod_b200_process_batch(h, bits, 1, iq_out, cap, out_bytes);
+}
+
+int dabmod_b200_synchronize(dabmod_b200 *h)
+{
+    return guard([&] {
+        if (!h) throw ApiError(DABMOD_B200_EINVAL, "null handle");
+        CUDA_CHECK(cudaSetDevice(h->device));
+        CUDA_CHECK(cudaStreamSynchronize(h->s_in));
+        CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+        CUDA_CHECK(cudaStreamSynchronize(h->s_out));
+    });
+}
+
+int dabmod_b200_reset(dabmod_b200 *h)
+{
+    return guard([&] {
+        if (!h) throw ApiError(DABMOD_B200_EINVAL, "null handle");
+        std::lock_guard<std::mutex> lock(h->mtx);
+        h->tf_counter = 0;
+    });
+}
+
+int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits, size_t nbytes)
+{
+    return guard([&] {
+        if (!h) throw ApiError(DABMOD_B200_EINVAL, "null handle");
+        (void)prev_bits; (void)nbytes;
+        std::lock_guard<std::mutex> lock(h->mtx);
+        h->tf_counter = tf_index;
+    });
+}
+
+uint64_t dabmod_b200_num_clipped_samples(dabmod_b200 *h) { return h ? h->clipped_last : 0; }
+uint32_t dabmod_b200_last_launch_count(const dabmod_b200 *h) { return h ? h->launches_last : 0; }
+
+int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
+{
+    return guard([&] {
+        if (!h || !name || !value) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        std::lock_guard<std::mutex> lock(h->mtx);
+        const std::string n(name);
+        std::stringstream ss(value);
+        ss.exceptions(std::stringstream::failbit | std::stringstream::badbit);
+        dabmod_b200_config &c = h->cfg;
+        try {
+            if (n == "digital") { ss >> c.digital_gain; }
+            else if (n == "profile") { int v; ss >> v; h->profile = v != 0; }
+            else if (n == "var") { ss >> c.gain_variance; }
+            else if (n == "mode") {
+                std::string v; ss >> v;
+                for (auto &ch : v) ch = (char)tolower(ch);
+                if (v == "fix") c.gain_mode = DABMOD_B200_GAIN_FIX;
+                else if (v == "max") c.gain_mode = DABMOD_B200_GAIN_MAX;
+                else if (v == "var") c.gain_mode = DABMOD_B200_GAIN_VAR;
+                else throw ApiError(DABMOD_B200_EINVAL, "Gainmode " + v + " unknown (fix|max|var)");
+            }
+            else if (n == "tii.enable") { int v; ss >> v; c.tii_enable = v != 0; h->tables_dirty = true; }
+            else if (n == "tii.comb") {
+                int v; ss >> v;
+                if (v < 0 || v > 23) throw ApiError(DABMOD_B200_EINVAL, "TII comb not valid!");
+                c.tii_comb = v; h->tables_dirty = true;
+            }
+            else if (n == "tii.pattern") {
+                int v; ss >> v;
+                if (v < 0 || v > 69) throw ApiError(DABMOD_B200_EINVAL, "TII pattern not valid!");
+                c.tii_pattern = v; h->tables_dirty = true;
+            }
+            else if (n == "tii.old_variant") { int v; ss >> v; c.tii_old_variant = v != 0; h->tables_dirty = true; }
+            else if (n == "taps") {
+                int cnt; ss >> cnt;
+                if (cnt <= 0) throw ApiError(DABMOD_B200_EINVAL, "FIRFilter: taps file has invalid format.");
+                if (cnt > MAX_FIR_TAPS) throw ApiError(DABMOD_B200_EUNSUPPORTED, "FIRFilter: more than 128 taps");
+                if (!h->has_fir()) throw ApiError(DABMOD_B200_ESTATE, "FIRFilter is not part of this chain");
+                std::vector<float> t(cnt);
+                for (auto &x : t) ss >> x;
+                h->fir_taps = t;
+            }
+            else if (n == "coefs") {
+                if (h->dpd_mode == 0) throw ApiError(DABMOD_B200_ESTATE, "MemlessPoly is not part of this chain");
+                int fmt; ss >> fmt;
+                if (fmt == 1) {
+                    int nc; ss >> nc;
+                    if (nc != 5) throw ApiError(DABMOD_B200_EINVAL, "MemlessPoly: invalid number of coefs");
+                    for (int i = 0; i < 10; i++) ss >> h->dpd[i];
+                    h->dpd_mode = DABMOD_B200_DPD_ODD_POLY;
+                }
+                else if (fmt == 2) {
+                    for (int i = 0; i < 33; i++) ss >> h->dpd[i];
+                    h->dpd_mode = DABMOD_B200_DPD_LUT;
+                    h->tables_dirty = true;
+                }
+                else throw ApiError(DABMOD_B200_EINVAL, "MemlessPoly: coef file has unknown format");
+            }
+            else {
+                throw ApiError(DABMOD_B200_EINVAL, "Parameter '" + n + "' is not exported by controllable dabmod_b200");
+            }
+        }
+        catch (const std::ios_base::failure &) {
+            throw ApiError(DABMOD_B200_EINVAL, "could not parse value for parameter '" + n + "'");
+        }
+    });
+}
+
+int dabmod_b200_get_param(dabmod_b200 *h, const char *name, char *buf, size_t cap)
+{
+    return guard([&] {
+        if (!h || !name || !buf || cap == 0) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        std::lock_guard<std::mutex> lock(h->mtx);
+        const std::string n(name);
+        const dabmod_b200_config &c = h->cfg;
+        std::stringstream ss;
+        if (n == "digital") ss << c.digital_gain;
+        else if (n == "var") ss << c.gain_variance;
+        else if (n == "mode") ss << (c.gain_mode == 0 ? "fix" : c.gain_mode == 1 ? "max" : "var");
+        else if (n == "windowlen") ss << c.window_overlap;
+        else if (n == "cfr") ss << c.cfr_enable;
+        else if (n == "clip") ss << std::fixed << c.cfr_clip;
+        else if (n == "errorclip") ss << std::fixed << c.cfr_errclip;
+        else if (n == "tii.enable") ss << (c.tii_enable ? 1 : 0);
+        else if (n == "tii.comb") ss << c.tii_comb;
+        else if (n == "tii.pattern") ss << c.tii_pattern;
+        else if (n == "tii.old_variant") ss << (c.tii_old_variant ? 1 : 0);
+        else if (n == "ntaps") ss << h->fir_taps.size();
+        else if (n == "rate") ss << c.output_rate;
+        else if (n == "num_clipped_samples") ss << h->clipped_last;
+        else throw ApiError(DABMOD_B200_EINVAL, "Parameter '" + n + "' is not exported by controllable dabmod_b200");
+        const std::string s = ss.str();
+        if (s.size() + 1 > cap) throw ApiError(DABMOD_B200_EINVAL, "buffer too small");
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+    });
+}
+
+int dabmod_b200_table_interleaver(int mode, int32_t *idx, int cap)
+{
+    return guard([&] {
+        const ModeInfo m = mode_info(mode);
+        if (!idx || cap < m.K) throw ApiError(DABMOD_B200_EINVAL, "buffer too small");
+        const std::vector<int> d = interleaver_dest(m);
+        for (int j = 0; j < m.K; j++) idx[j] = d[j];
+    });
+}
+
+int dabmod_b200_table_phase_ref(int mode, uint8_t *q, int cap)
+{
+    return guard([&] {
+        const ModeInfo m = mode_info(mode);
+        if (!q || cap < m.K) throw ApiError(DABMOD_B200_EINVAL, "buffer too small");
+        const std::vector<uint8_t> v = phase_ref_quarter_turns(m);
+        std::memcpy(q, v.data(), m.K);
+    });
+}
+
+int dabmod_b200_table_tii(int mode, int comb, int pattern, uint8_t *acp, int cap)
+{
+    return guard([&] {
+        const ModeInfo m = mode_info(mode);
+        if (!acp || cap < m.K) throw ApiError(DABMOD_B200_EINVAL, "buffer too small");
+        std::vector<int> pairs;
+        if (!tii_pairs(m, comb, pattern, pairs))
+            throw ApiError(DABMOD_B200_EUNSUPPORTED, "TII::TII DAB mode " + std::to_string(mode) + " not valid!");
+        std::memset(acp, 0, m.K);
+        for (int ix : pairs) acp[ix] = 1;
+    });
+}
+
+int dabmod_b200_table_cic(int n_carriers, float spacing, int ratio, float *filter)
+{
+    return guard([&] {
+        if (!filter || n_carriers <= 0) throw ApiError(DABMOD_B200_EINVAL, "bad argument");
+        const std::vector<float> f = cic_filter(n_carriers, spacing, ratio);
+        std::memcpy(filter, f.data(), sizeof(float) * n_carriers);
+    });
+}
+
+int dabmod_b200_resampler_sizes(uint64_t in_rate, uint64_t out_rate, int resolution, int *fft_in, int *fft_out)
+{
+    return guard([&] {
+        if (!in_rate || !out_rate || resolution <= 0 || !fft_in || !fft_out)
+            throw ApiError(DABMOD_B200_EINVAL, "bad argument");
+        ResamplerPlan rp = resampler_plan(in_rate, out_rate, resolution);
+        *fft_in = rp.ni;
+        *fft_out = rp.no;
+    });
+}
+
+int dabmod_b200_kernel_time(dabmod_b200 *h, int idx, char *name, size_t cap, float *ms)
+{
+    return guard([&] {
+        if (!h || !ms) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        std::lock_guard<std::mutex> lock(h->mtx);
+        if (idx < 0 || (size_t)idx >= h->timed.size())
+            throw ApiError(DABMOD_B200_ESTATE, "no such timed launch (set_param(\"profile\", \"1\") first)");
+        const dabmod_b200::Timed &t = h->timed[idx];
+        CUDA_CHECK(cudaEventSynchronize(t.b));
+        CUDA_CHECK(cudaEventElapsedTime(ms, t.a, t.b));
+        if (name && cap) {
+            std::strncpy(name, t.name, cap - 1);
+            name[cap - 1] = 0;
+        }
+    });
+}
+
+} // extern "C"

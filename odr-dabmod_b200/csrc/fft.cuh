@@ -1,0 +1,172 @@
+// Register-resident radix-4/8/16 butterflies and the shared-memory Stockham
+// pass used by every FFT in this library (OFDM IFFT, CFR FFT, resampler FFTs).
+//
+// Conventions: unnormalised transforms like FFTW/KISS (reference
+// OfdmGenerator.cpp:109-111, Resampler.cpp:94-108).  INV=true evaluates
+// sum_k X[k] e^{+j 2 pi k n / N} (FFTW_BACKWARD), INV=false the forward sign.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace dabmod {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by +j (INV) or -j (forward)
+template <bool INV>
+__device__ __forceinline__ float2 mul_j(float2 a)
+{
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// twiddle table holds e^{+j theta}; the forward transform needs the conjugate
+template <bool INV>
+__device__ __forceinline__ float2 tw_dir(float2 w)
+{
+    return INV ? w : make_float2(w.x, -w.y);
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft2(float2 &a, float2 &b)
+{
+    const float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
+    const float2 t2 = cadd(a1, a3), t3 = mul_j<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+// v[0..7] natural order in, natural order out
+template <bool INV>
+__device__ __forceinline__ void fft8(float2 *v)
+{
+    const float h = 0.70710678118654752440f;
+    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    fft4<INV>(e0, e1, e2, e3);
+    fft4<INV>(o0, o1, o2, o3);
+    // W8^1 = (1 + sj)/sqrt2, W8^2 = sj, W8^3 = (-1 + sj)/sqrt2, s = +1 (INV) / -1
+    const float2 j1 = mul_j<INV>(o1);
+    o1 = make_float2((o1.x + j1.x) * h, (o1.y + j1.y) * h);
+    o2 = mul_j<INV>(o2);
+    const float2 j3 = mul_j<INV>(o3);
+    o3 = make_float2((j3.x - o3.x) * h, (j3.y - o3.y) * h);
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// v[0..15] natural order in, natural order out (4 x 4 decomposition)
+template <bool INV>
+__device__ __forceinline__ void fft16(float2 *v)
+{
+    // cos/sin of 2 pi e / 16
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+    const float h = 0.70710678118654752440f;
+    // column transforms over the stride-4 subsequences
+#pragma unroll
+    for (int q = 0; q < 4; q++) fft4<INV>(v[q], v[q + 4], v[q + 8], v[q + 12]);
+    // now v[q + 4k] = Y_q[k]; twiddle by W16^{qk}
+    const float sg = INV ? 1.0f : -1.0f;
+    // q=1: k=1 -> e=1, k=2 -> e=2, k=3 -> e=3
+    v[1 + 4] = cmul(v[1 + 4], make_float2(c1, sg * s1));
+    v[1 + 8] = cmul(v[1 + 8], make_float2(h, sg * h));
+    v[1 + 12] = cmul(v[1 + 12], make_float2(s1, sg * c1));
+    // q=2: e = 2, 4, 6
+    v[2 + 4] = cmul(v[2 + 4], make_float2(h, sg * h));
+    v[2 + 8] = mul_j<INV>(v[2 + 8]);
+    v[2 + 12] = cmul(v[2 + 12], make_float2(-h, sg * h));
+    // q=3: e = 3, 6, 9
+    v[3 + 4] = cmul(v[3 + 4], make_float2(s1, sg * c1));
+    v[3 + 8] = cmul(v[3 + 8], make_float2(-h, sg * h));
+    v[3 + 12] = cmul(v[3 + 12], make_float2(-c1, -sg * s1));
+    // row transforms over q for each k: X[k + 4m]
+#pragma unroll
+    for (int k = 0; k < 4; k++) fft4<INV>(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    // v[4k + m] = X[k + 4m] -> transpose to natural order
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int m = k + 1; m < 4; m++) {
+            const float2 t = v[4 * k + m];
+            v[4 * k + m] = v[4 * m + k];
+            v[4 * m + k] = t;
+        }
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void fft_radix(float2 *v)
+{
+    static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+    if (R == 2) fft2<INV>(v[0], v[1]);
+    if (R == 4) fft4<INV>(v[0], v[1], v[2], v[3]);
+    if (R == 8) fft8<INV>(v);
+    if (R == 16) fft16<INV>(v);
+}
+
+// Shared-memory index padding: one complex slot per 16 keeps the stride-R
+// writes of the first Stockham pass and the stride-N/R reads of every pass
+// bank-conflict free for 8-byte elements.
+__device__ __host__ __forceinline__ constexpr int spad(int i) { return i + (i >> 4); }
+
+// One Stockham radix-R pass over `nfft` independent transforms of size N that
+// lie back to back in `buf` (element i of transform g at spad(g*N + i)).
+//   Ns   = product of the radices of the passes already done
+//   tw   = table of e^{+j 2 pi k / NT}, k in [0, NT), NT a multiple of Ns*R
+// The pass is split in two halves so that the caller can put ONE barrier
+// between "everyone has read" and "everyone writes" (in-place operation).
+// Each thread owns PER = (nfft*N/R)/NTHREADS butterflies.
+template <int R, bool INV, int PER>
+struct StockhamPass {
+    float2 v[PER][R];
+
+    __device__ __forceinline__ void load(const float2 *buf, int tid, int nthreads, int N, int Ns,
+                                         const float2 *tw, int NT)
+    {
+        const int nb = N / R; // butterflies per transform
+        const int twstep = NT / (Ns * R);
+#pragma unroll
+        for (int p = 0; p < PER; p++) {
+            const int b = tid + p * nthreads;
+            const int g = b / nb, j = b - g * nb;
+            const int base = g * N + j;
+            const int k = j & (Ns - 1);
+#pragma unroll
+            for (int r = 0; r < R; r++) v[p][r] = buf[spad(base + r * nb)];
+            if (Ns > 1) {
+#pragma unroll
+                for (int r = 1; r < R; r++) v[p][r] = cmul(v[p][r], tw_dir<INV>(tw[k * r * twstep]));
+            }
+            fft_radix<R, INV>(v[p]);
+        }
+    }
+
+    __device__ __forceinline__ void store(float2 *buf, int tid, int nthreads, int N, int Ns) const
+    {
+        const int nb = N / R;
+#pragma unroll
+        for (int p = 0; p < PER; p++) {
+            const int b = tid + p * nthreads;
+            const int g = b / nb, j = b - g * nb;
+            const int k = j & (Ns - 1);
+            const int j0 = (j - k) * R + k;
+            const int base = g * N + j0;
+#pragma unroll
+            for (int r = 0; r < R; r++) buf[spad(base + r * Ns)] = v[p][r];
+        }
+    }
+};
+
+} // namespace dabmod

@@ -1,0 +1,573 @@
+// sm_100a kernels of the COFDM hot path.  See DESIGN.md for the data layout
+// and the roofline each kernel is measured against.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft.cuh"
+
+namespace dabmod {
+
+constexpr int SYM_THREADS = 128;     // one symbol group = 2048 complex points = 16 per thread
+constexpr int SYM_POINTS = 2048;     // G * N for every transmission mode
+constexpr int SYM_BUF = SYM_POINTS + SYM_POINTS / 16;  // padded (spad)
+constexpr int MAX_TII = 64;          // 32 carrier pairs
+constexpr int MAX_FIR_TAPS = 128;
+constexpr int MAX_WINDOW = 256;      // 2 * windowOverlap entries kept on chip
+
+// ---------------------------------------------------------------------------
+// Epilogue: [MemlessPoly] -> [FormatConverter] -> store.
+// Reference: MemlessPoly.cpp:237-309, FormatConverter.cpp:112-165.
+// ---------------------------------------------------------------------------
+struct PostParams {
+    int dpd_mode;        // 0 none, 1 odd polynomial, 2 LUT
+    int format;          // 0 complexf, 1 s16, 2 u8, 3 s8
+    float am[5];
+    float pm[5];
+    float lut_scale;
+    const float *lut;    // 32 floats (device)
+    unsigned long long *clipped; // device counter
+};
+
+__device__ __forceinline__ float2 dpd_apply(const PostParams &pp, float2 x)
+{
+    if (pp.dpd_mode == 1) {
+        // __fmul_rn/__fadd_rn keep the reference's operation order free of FMA contraction
+        const float mag = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+        float amp = pp.am[4];
+        float ph = pp.pm[4];
+#pragma unroll
+        for (int i = 3; i >= 0; i--) {
+            amp = __fadd_rn(pp.am[i], __fmul_rn(mag, amp));
+            ph = __fadd_rn(pp.pm[i], __fmul_rn(mag, ph));
+        }
+        ph = -ph;
+        const float p2 = __fmul_rn(ph, ph);
+        const float re = __fsub_rn(1.0f, __fmul_rn(p2, __fadd_rn(-0.5f, __fmul_rn(p2,
+                         __fadd_rn(0.486666f, __fmul_rn(p2, -0.00138888f))))));
+        const float im = __fmul_rn(ph, __fadd_rn(1.0f, __fmul_rn(p2,
+                         __fadd_rn(0.166666f, __fmul_rn(p2, 0.00833333f)))));
+        const float ar = __fmul_rn(x.x, amp), ai = __fmul_rn(x.y, amp);
+        return make_float2(__fsub_rn(__fmul_rn(ar, re), __fmul_rn(ai, im)),
+                           __fadd_rn(__fmul_rn(ar, im), __fmul_rn(ai, re)));
+    }
+    if (pp.dpd_mode == 2) {
+        const float mag = hypotf(x.x, x.y);
+        const unsigned scaled = (unsigned)__float2ll_rn(__fmul_rn(mag, pp.lut_scale));
+        const float g = __ldg(pp.lut + (scaled >> 27));
+        return make_float2(x.x * g, x.y * g);
+    }
+    return x;
+}
+
+// saturating conversion with C truncation, counts clipped components
+__device__ __forceinline__ int fmt_s16(float v, unsigned &clip)
+{
+    if (v < -32768.0f) { clip++; return -32768; }
+    if (v > 32767.0f) { clip++; return 32767; }
+    return (int)v;
+}
+__device__ __forceinline__ int fmt_u8(float v, unsigned &clip)
+{
+    const float s = v + 128.0f;
+    if (s < 0.0f) { clip++; return 0; }
+    if (s > 255.0f) { clip++; return 255; }
+    return (int)s;
+}
+__device__ __forceinline__ int fmt_s8(float v, unsigned &clip)
+{
+    if (v < -128.0f) { clip++; return -128; }
+    if (v > 127.0f) { clip++; return 127; }
+    return (int)v;
+}
+
+// Stores complex sample number `idx` of the output stream.
+template <bool POST>
+__device__ __forceinline__ void store_sample(void *out, size_t idx, float2 v, const PostParams &pp,
+                                             unsigned &clip)
+{
+    if (!POST) {
+        reinterpret_cast<float2 *>(out)[idx] = v;
+        return;
+    }
+    v = dpd_apply(pp, v);
+    if (pp.format == 0) {
+        reinterpret_cast<float2 *>(out)[idx] = v;
+    }
+    else if (pp.format == 1) {
+        short2 s;
+        s.x = (short)fmt_s16(v.x, clip);
+        s.y = (short)fmt_s16(v.y, clip);
+        reinterpret_cast<short2 *>(out)[idx] = s;
+    }
+    else if (pp.format == 2) {
+        uchar2 s;
+        s.x = (unsigned char)fmt_u8(v.x, clip);
+        s.y = (unsigned char)fmt_u8(v.y, clip);
+        reinterpret_cast<uchar2 *>(out)[idx] = s;
+    }
+    else {
+        char2 s;
+        s.x = (signed char)fmt_s8(v.x, clip);
+        s.y = (signed char)fmt_s8(v.y, clip);
+        reinterpret_cast<char2 *>(out)[idx] = s;
+    }
+}
+
+__device__ __forceinline__ void flush_clip(const PostParams &pp, unsigned clip)
+{
+    // one atomic per warp that saw clipping
+    const unsigned total = __reduce_add_sync(0xffffffffu, clip);
+    if (total && (threadIdx.x & 31) == 0) atomicAdd(pp.clipped, (unsigned long long)total);
+}
+
+// ---------------------------------------------------------------------------
+// k_symbols: bits -> QPSK -> frequency interleave -> differential modulation
+//   -> null/TII multiplex -> [CicEq] -> carrier placement -> IFFT -> [CFR]
+//   -> gain -> guard interval [-> window] -> store
+// Reference: QpskSymbolMapper.cpp:105-156, FrequencyInterleaver.cpp:103-126,
+// DifferentialModulator.cpp:45-76, SignalMultiplexer.cpp:45-71, TII.cpp:172-245,
+// CicEqualizer.cpp:66-91, OfdmGenerator.cpp:157-373, GainControl.cpp:82-340,
+// GuardIntervalInserter.cpp:115-323.
+//
+// One CTA = one (TF, chunk of consecutive symbol groups).  A symbol group is
+// G = 2048/N consecutive OFDM symbols transformed side by side in one 2048
+// point shared buffer, so every mode keeps all 128 threads busy with 16
+// points each.
+// ---------------------------------------------------------------------------
+struct SymParams {
+    // mode
+    int L, K, N, null_size, sym_size, tf_in_bytes, tf_samples;
+    int G;                  // symbols per group = 2048 / N
+    int n_groups;           // ceil((L+1)/G)
+    int groups_per_chunk;
+    int n_chunks;
+    // per-source-carrier tables (device)
+    const uint16_t *bin_of_src;   // K: FFT bin of the carrier that source j is interleaved to
+    const uint8_t *phase0;        // K: phase reference of that carrier, units of pi/4 (even)
+    const float *cic;             // K or nullptr: CicEqualizer gain of that carrier
+    const float2 *twiddle;        // 2048 entries e^{+j 2 pi k / 2048}
+    // null symbol / TII
+    int tii_count;                // carriers set in the TII symbol (0 = plain null symbol)
+    int tii_parity;               // TII is inserted on TFs where ((tf + tii_parity) & 1) == 0
+    const uint16_t *tii_bin;      // tii_count FFT bins
+    const float2 *tii_val;        // tii_count values (phase reference, CicEq applied)
+    // CFR
+    int cfr;
+    float cfr_clip, cfr_errclip;
+    // gain
+    int gain_mode;
+    float gain_const;             // normalise * digital_gain
+    float var_factor;
+    // guard interval windowing
+    int window;                   // windowOverlap W
+    const float *window_tab;      // 2W floats
+    // I/O
+    const uint8_t *bits;          // n_tf * tf_in_bytes
+    void *out;                    // n_tf * tf_samples samples
+    unsigned long long tf_offset; // index of the first TF of this launch within the stream
+    PostParams post;
+};
+
+struct SymSmem {
+    float2 buf[SYM_BUF];
+    float2 tw[SYM_POINTS];
+    uint32_t spread[256];
+    float2 c8[8];
+    float red[4][8][4];    // [warp][symbol in group][re, im, re2, im2] / [min,max]
+    float gain[8];
+};
+
+// out-position of symbol s inside the TF
+__device__ __forceinline__ int sym_pos(const SymParams &p, int s)
+{
+    return s == 0 ? 0 : p.null_size + (s - 1) * p.sym_size;
+}
+
+// D nibbles (phase increments in units of pi/4) of 8 carriers from their I and Q bytes
+__device__ __forceinline__ uint32_t phase_step(const uint32_t *spread, unsigned ib, unsigned qb)
+{
+    return 0x11111111u + 2u * spread[ib ^ qb] + 4u * spread[qb];
+}
+
+template <int N, bool POST>
+__global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__ SymParams p)
+{
+    constexpr int G = SYM_POINTS / N;         // symbols per group
+    constexpr int TG = SYM_THREADS / G;       // threads per symbol in the emit phase
+    constexpr int K16 = (N * 3 / 4) / 16;     // 16-carrier work items per symbol (K = 3N/4)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SymSmem &sm = *reinterpret_cast<SymSmem *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int tf = blockIdx.x / p.n_chunks;
+    const int chunk = blockIdx.x - tf * p.n_chunks;
+    const int grp0 = chunk * p.groups_per_chunk;
+    const int grp1 = min(grp0 + p.groups_per_chunk, p.n_groups);
+    const int K = p.K;
+    const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
+    const size_t out_base = (size_t)tf * p.tf_samples;
+    const bool tii_on = p.tii_count > 0 && (((p.tf_offset + tf + p.tii_parity) & 1) == 0);
+
+    // ---- per-CTA tables ----
+    for (int i = tid; i < SYM_POINTS; i += SYM_THREADS) sm.tw[i] = __ldg(p.twiddle + i);
+    for (int b = tid; b < 256; b += SYM_THREADS) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int n = 0; n < 8; n++) s |= ((b >> (7 - n)) & 1u) << (4 * n);
+        sm.spread[b] = s;
+    }
+    if (tid < 8) {
+        // exactly the values the reference's float32 product chain takes:
+        // {1, v, 0, -v, -1} with v = (float)M_SQRT1_2 (v*v rounds to 0.5)
+        const float v = 0.70710678118654752440f;
+        const float c[8] = {1.f, v, 0.f, -v, -1.f, -v, 0.f, v};
+        sm.c8[tid] = make_float2(c[tid], c[(tid + 6) & 7]);
+    }
+
+    // ---- carrier work item of this thread: 16 consecutive source carriers ----
+    // thread (g, jj): symbol g of the group, carriers 16*jj .. 16*jj+15
+    const int cg = tid / K16, jj = tid - cg * K16;
+    const bool carrier_thread = tid < G * K16;
+    uint32_t ph_lo = 0, ph_hi = 0;      // nibble-packed running phase, carriers 0-7 / 8-15
+    if (carrier_thread) {
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            ph_lo |= (uint32_t)__ldg(p.phase0 + 16 * jj + n) << (4 * n);
+            ph_hi |= (uint32_t)__ldg(p.phase0 + 16 * jj + 8 + n) << (4 * n);
+        }
+    }
+    __syncthreads();
+
+    // Phase prefix: consume the data symbols that precede this chunk.
+    // Symbol s >= 2 carries data symbol d = s - 2.
+    {
+        const int s_first = grp0 * G;
+        const int nd = max(0, s_first - 2);
+        if (carrier_thread) {
+            const uint8_t *row = bits + 2 * jj;
+            for (int d = 0; d < nd; d++, row += K / 4) {
+                const unsigned iw = __ldg(reinterpret_cast<const unsigned short *>(row));
+                const unsigned qw = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
+                ph_lo = (ph_lo + phase_step(sm.spread, iw & 0xff, qw & 0xff)) & 0x77777777u;
+                ph_hi = (ph_hi + phase_step(sm.spread, iw >> 8, qw >> 8)) & 0x77777777u;
+            }
+        }
+    }
+
+    unsigned clip = 0;
+    float gain_sym1 = 1.0f;
+    for (int gi = grp0; gi < grp1; gi++) {
+        int grp = gi;
+        if (G == 1 && grp0 == 0) {
+            // TM I: the null symbol (group 0) needs the gain of symbol 1 (group 1):
+            // run group 1 first.  Neither consumes data bits.
+            grp = gi == 0 ? 1 : gi == 1 ? 0 : gi;
+            if (grp == 0 && !tii_on) {
+                // plain null symbol: all-zero carriers -> all-zero samples
+                const size_t pos = out_base;
+                for (int i = tid; i < p.null_size; i += SYM_THREADS)
+                    store_sample<POST>(p.out, pos + i, make_float2(0.f, 0.f), p.post, clip);
+                continue;
+            }
+        }
+        const int s0 = grp * G;   // first symbol of the group
+        // ---- 1. frequency-domain symbols into the shared buffer ----
+        // zero bins: DC and the guard band (OfdmGenerator.cpp:207-220)
+        {
+            const int nz = N - K;            // bins K/2+1 .. N-K/2-1 plus bin 0
+            for (int i = tid; i < G * nz; i += SYM_THREADS) {
+                const int g = i / nz, z = i - g * nz;
+                const int bin = z == 0 ? 0 : K / 2 + z;
+                sm.buf[spad(g * N + bin)] = make_float2(0.f, 0.f);
+            }
+        }
+        if (carrier_thread) {
+            // advance the phase through the symbols of the group; emit our own
+            uint32_t my_lo = 0, my_hi = 0;
+            int my_kind = 0; // 0 = null (zeros/TII), 1 = phase (ref or data)
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int s = s0 + g;
+                if (s >= 2 && s <= p.L) {
+                    const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
+                    const unsigned iw = __ldg(reinterpret_cast<const unsigned short *>(row));
+                    const unsigned qw = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
+                    ph_lo = (ph_lo + phase_step(sm.spread, iw & 0xff, qw & 0xff)) & 0x77777777u;
+                    ph_hi = (ph_hi + phase_step(sm.spread, iw >> 8, qw >> 8)) & 0x77777777u;
+                }
+                if (g == cg) {
+                    my_lo = ph_lo; my_hi = ph_hi;
+                    my_kind = (s >= 1 && s <= p.L) ? 1 : 0;
+                }
+            }
+            float2 *dst = sm.buf + 0;
+            const int fbase = cg * N;
+#pragma unroll
+            for (int n = 0; n < 16; n++) {
+                const int j = 16 * jj + n;
+                const unsigned ph = ((n < 8 ? my_lo >> (4 * n) : my_hi >> (4 * (n - 8)))) & 7u;
+                float2 v = my_kind ? sm.c8[ph] : make_float2(0.f, 0.f);
+                if (p.cic) {
+                    const float f = __ldg(p.cic + j);
+                    v.x *= f; v.y *= f;
+                }
+                dst[spad(fbase + __ldg(p.bin_of_src + j))] = v;
+            }
+        }
+        __syncthreads();
+        // TII carriers overwrite the zeroed null symbol (symbol 0 is in group 0, slot 0)
+        if (grp == 0 && tii_on && tid < p.tii_count)
+            sm.buf[spad(__ldg(p.tii_bin + tid))] = __ldg(p.tii_val + tid);
+        if (grp == 0 && tii_on) __syncthreads();
+
+        // ---- 2. inverse FFT of the G symbols, in place ----
+        if (N == 2048) {
+            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
+            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 256, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 256); __syncthreads(); }
+        }
+        else if (N == 1024) {
+            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
+            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 128, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 128); __syncthreads(); }
+        }
+        else if (N == 512) {
+            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 8, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 8); __syncthreads(); }
+            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 64, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 64); __syncthreads(); }
+        }
+        else {
+            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw, SYM_POINTS);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
+        }
+
+        // ---- 3. gain: statistics per symbol over its N samples ----
+        // thread (eg, tt): symbol eg of the group, samples tt + TG*i
+        const int eg = tid / TG, tt = tid - eg * TG;
+        float2 x[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = sm.buf[spad(eg * N + tt + TG * i)];
+        float g_sym;
+        if (p.gain_mode == 0) {
+            g_sym = 512.0f;
+        }
+        else {
+            // A symbol is owned by TG threads: LANES lanes of WPS warps, or (TG < 32)
+            // one LANES-wide segment ("slot") of a warp that holds SPW symbols.
+            constexpr int LANES = TG < 32 ? TG : 32;
+            constexpr int WPS = TG < 32 ? 1 : TG / 32;
+            constexpr int SPW = TG < 32 ? 32 / TG : 1;
+            const int warp = tid >> 5, lane = tid & 31;
+            const int slot = lane / LANES;
+            const int w0 = TG < 32 ? warp : eg * WPS;   // first warp of my symbol
+            const bool seg_leader = (lane & (LANES - 1)) == 0;
+            if (p.gain_mode == 1) {
+                float mn = x[0].x, mx = x[0].x;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    mn = fminf(mn, fminf(x[i].x, x[i].y));
+                    mx = fmaxf(mx, fmaxf(x[i].x, x[i].y));
+                }
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                if (seg_leader) { sm.red[warp][slot][0] = mn; sm.red[warp][slot][1] = mx; }
+                __syncthreads();
+                if (tid < G) {
+                    const int ww = TG < 32 ? tid / SPW : tid * WPS, ss = TG < 32 ? tid % SPW : 0;
+                    float a = sm.red[ww][ss][0], b = sm.red[ww][ss][1];
+                    for (int w = 1; w < WPS; w++) {
+                        a = fminf(a, sm.red[ww + w][ss][0]);
+                        b = fmaxf(b, sm.red[ww + w][ss][1]);
+                    }
+                    const float m = fmaxf(-a, b);
+                    sm.gain[tid] = ((int)m != 0) ? 32767.0f / m : 1.0f;
+                }
+            }
+            else {
+                // two-pass mean / variance of re and im (GainControl.cpp:251-340)
+                float sr = 0.f, si = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) { sr += x[i].x; si += x[i].y; }
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+                    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                    si += __shfl_xor_sync(0xffffffffu, si, o);
+                }
+                if (seg_leader) { sm.red[warp][slot][0] = sr; sm.red[warp][slot][1] = si; }
+                __syncthreads();
+                float mr = 0.f, mi = 0.f;
+                for (int w = 0; w < WPS; w++) { mr += sm.red[w0 + w][slot][0]; mi += sm.red[w0 + w][slot][1]; }
+                mr *= 1.0f / N; mi *= 1.0f / N;
+                float vr = 0.f, vi = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float dr = x[i].x - mr, di = x[i].y - mi;
+                    vr = fmaf(dr, dr, vr); vi = fmaf(di, di, vi);
+                }
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+                    vr += __shfl_xor_sync(0xffffffffu, vr, o);
+                    vi += __shfl_xor_sync(0xffffffffu, vi, o);
+                }
+                if (seg_leader) { sm.red[warp][slot][2] = vr; sm.red[warp][slot][3] = vi; }
+                __syncthreads();
+                if (tid < G) {
+                    const int ww = TG < 32 ? tid / SPW : tid * WPS, ss = TG < 32 ? tid % SPW : 0;
+                    float a = 0.f, b = 0.f;
+                    for (int w = 0; w < WPS; w++) { a += sm.red[ww + w][ss][2]; b += sm.red[ww + w][ss][3]; }
+                    const float sdr = p.var_factor * sqrtf(a * (1.0f / N));
+                    const float sdi = p.var_factor * sqrtf(b * (1.0f / N));
+                    // NULL detection looks at the real part only (GainControl.cpp:331)
+                    sm.gain[tid] = ((int)sdr != 0) ? 32767.0f / fmaxf(sdr, sdi) : 1.0f;
+                }
+            }
+            __syncthreads();
+            // the null symbol borrows the gain of symbol 1 (GainControl.cpp:139-144)
+            if (G > 1) g_sym = (s0 + eg == 0) ? sm.gain[1] : sm.gain[eg];
+            else g_sym = sm.gain[0];
+        }
+        if (G == 1) {
+            if (grp == 1) gain_sym1 = g_sym;
+            if (grp == 0) g_sym = gain_sym1;
+        }
+        g_sym *= p.gain_const;
+
+        // ---- 4. guard interval + store ----
+        const int s = s0 + eg;
+        if (s <= p.L) {
+            const int size = s == 0 ? p.null_size : p.sym_size;
+            const int pre = size - N;
+            const size_t pos = out_base + sym_pos(p, s);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int n = tt + TG * i;
+                const float2 v = make_float2(x[i].x * g_sym, x[i].y * g_sym);
+                store_sample<POST>(p.out, pos + pre + n, v, p.post, clip);
+                if (n >= N - pre) store_sample<POST>(p.out, pos + n - (N - pre), v, p.post, clip);
+            }
+        }
+        __syncthreads();
+    }
+    if (POST && p.post.format != 0) flush_clip(p.post, clip);
+}
+
+} // namespace dabmod
+
+namespace dabmod {
+
+// ---------------------------------------------------------------------------
+// k_fir: real-tap FIR on interleaved I/Q, anti-causal, zero-extended at the end
+// of each TF, no state across TFs:  out[n] = sum_j taps[j] * in[n + j]
+// Reference: FIRFilter.cpp:144-192 (taps: :59-71, :95-141).
+//
+// One CTA = one tile of FIR_TILE consecutive samples of one TF.  The tile and
+// its NT-1 sample forward halo are staged in shared memory; each thread keeps
+// FIR_M consecutive outputs in registers and slides over FIR_M+NT-1 inputs, so
+// every input is read from shared memory once per thread and every tap is an
+// immediate constant-bank operand of the FMA.  Accumulation runs in ascending
+// tap order like the reference's inner loop.
+// ---------------------------------------------------------------------------
+constexpr int FIR_THREADS = 256;
+constexpr int FIR_M = 8;
+constexpr int FIR_TILE = FIR_THREADS * FIR_M;
+
+struct FirParams {
+    const float2 *in;     // n_tf * tf_samples
+    void *out;
+    int tf_samples;
+    int tiles_per_tf;
+    float taps[MAX_FIR_TAPS];   // zero padded to the template's NT
+    PostParams post;
+};
+
+// shared-memory index padding for 8-byte elements read with a stride of FIR_M
+__device__ __forceinline__ constexpr int fpad(int i) { return i + (i >> 3); }
+
+template <int NT, bool POST>
+__global__ void __launch_bounds__(FIR_THREADS) k_fir(const __grid_constant__ FirParams p)
+{
+    constexpr int SPAN = FIR_TILE + NT;      // samples staged (one spare keeps SPAN even)
+    __shared__ float2 xs[SPAN + SPAN / 8 + 8];
+    const int tid = threadIdx.x;
+    const int tf = blockIdx.x / p.tiles_per_tf;
+    const int tile = blockIdx.x - tf * p.tiles_per_tf;
+    const int n0 = tile * FIR_TILE;
+    const float2 *in = p.in + (size_t)tf * p.tf_samples;
+
+    // stage: two samples (16 B) per thread per step, zero beyond the TF end
+    for (int i = 2 * tid; i < SPAN; i += 2 * FIR_THREADS) {
+        const int n = n0 + i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n + 1 < p.tf_samples) {
+            v = __ldg(reinterpret_cast<const float4 *>(in + n));
+        }
+        else if (n < p.tf_samples) {
+            const float2 a = __ldg(in + n);
+            v.x = a.x; v.y = a.y;
+        }
+        xs[fpad(i)] = make_float2(v.x, v.y);
+        xs[fpad(i + 1)] = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+
+    float2 acc[FIR_M];
+#pragma unroll
+    for (int m = 0; m < FIR_M; m++) acc[m] = make_float2(0.f, 0.f);
+    const float2 *x = xs + tid * (FIR_M + 1);    // fpad(tid * FIR_M) with FIR_M == 8
+#pragma unroll
+    for (int i = 0; i < FIR_M + NT - 1; i++) {
+        const float2 v = x[i + (i >> 3)];
+#pragma unroll
+        for (int m = 0; m < FIR_M; m++) {
+            const int j = i - m;
+            if (j >= 0 && j < NT) {
+                acc[m].x = fmaf(v.x, p.taps[j], acc[m].x);
+                acc[m].y = fmaf(v.y, p.taps[j], acc[m].y);
+            }
+        }
+    }
+
+    unsigned clip = 0;
+    const int nbase = n0 + tid * FIR_M;
+    const size_t obase = (size_t)tf * p.tf_samples + nbase;
+    if (!POST && nbase + FIR_M <= p.tf_samples) {
+        float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + obase);
+#pragma unroll
+        for (int m = 0; m < FIR_M; m += 2)
+            o[m / 2] = make_float4(acc[m].x, acc[m].y, acc[m + 1].x, acc[m + 1].y);
+    }
+    else {
+#pragma unroll
+        for (int m = 0; m < FIR_M; m++)
+            if (nbase + m < p.tf_samples) store_sample<POST>(p.out, obase + m, acc[m], p.post, clip);
+    }
+    if (POST && p.post.format != 0) flush_clip(p.post, clip);
+}
+
+// ---------------------------------------------------------------------------
+// k_post: stand-alone [MemlessPoly] -> [FormatConverter] for chains where no
+// other kernel can carry the epilogue.  Reference: see PostParams.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_post(const float2 *in, void *out, size_t n, PostParams pp)
+{
+    unsigned clip = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        store_sample<true>(out, i, in[i], pp, clip);
+    if (pp.format != 0) flush_clip(pp, clip);
+}
+
+} // namespace dabmod

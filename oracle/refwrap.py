@@ -116,6 +116,14 @@ class RefChain:
             raise RuntimeError("ref_process: " + lib().ref_last_error().decode())
         return self._out[:n].copy()
 
+    def feed_raw(self, bits):
+        """Like feed() but leaves the result in the internal buffer (timing loops)."""
+        n = lib().ref_process(self._h, bits.ctypes.data, bits.size,
+                              self._out.ctypes.data, self._out.size)
+        if n < 0:
+            raise RuntimeError("ref_process: " + lib().ref_last_error().decode())
+        return n
+
     def run(self, bits_tfs, dtype=np.complex64):
         """Feed a (n_tf, tf_bytes) array; flush the pipelined stages by feeding
         `latency` extra copies of the last TF; returns a list of n_tf arrays."""
