@@ -227,7 +227,11 @@ def gpu_arm(args):
     d_bits = [host_bits.to("cuda", non_blocking=True).clone() for _ in range(4)]
     d_out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
     host_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the C ABI takes it as a cudaStream_t and the
+    # timing events below are recorded on the same stream the kernels run on
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
+    torch.cuda.synchronize()
 
     def step_device(i):
         mod.process_batch_device(d_bits[i % 4].data_ptr(), n_tf, d_out.data_ptr(), stream.cuda_stream)
