@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "resample.cuh"
 #include "tables.h"
 
 using namespace dabmod;
@@ -111,6 +112,18 @@ struct dabmod_b200 {
     DevBuf<uint8_t> d_bits;
     DevBuf<unsigned char> d_out;
     DevBuf<float2> d_tmp;          // symbol-stage output when another kernel follows
+    DevBuf<float2> d_tmp2;         // FIR output when the resampler follows
+
+    // resampler (Resampler.cpp:51-112)
+    bool has_res = false;
+    ResamplerPlan rp{};
+    std::vector<unsigned char> rad_in, rad_out;
+    DevBuf<float> d_res_win;
+    DevBuf<float2> d_tw_in, d_tw_out;
+    DevBuf<float2> d_hist;         // last Ni input samples of the stream (zeros at stream start)
+    DevBuf<float2> d_scratch;
+    int res_grid = 0;
+    size_t res_smem = 0;
 
     uint64_t clipped_last = 0;
     uint32_t launches_last = 0;
@@ -131,7 +144,10 @@ struct dabmod_b200 {
         return event_pool[events_used++];
     }
 
-    size_t out_samples_per_tf() const { return (size_t)m.tf_samples; }
+    size_t out_samples_per_tf() const
+    {
+        return has_res ? (size_t)m.tf_samples * rp.L / rp.M : (size_t)m.tf_samples;
+    }
     size_t out_bytes_per_tf() const { return out_samples_per_tf() * format_bytes(cfg.format); }
     bool has_fir() const { return !fir_taps.empty(); }
     bool has_post() const { return dpd_mode != 0 || cfg.format != DABMOD_B200_FMT_COMPLEXF; }
@@ -260,15 +276,28 @@ struct ProfScope {
     }
 };
 
-// Enqueue the kernel family for n_tf TFs: d_bits -> d_out.  `tf0` = index of
-// the first TF within the handle's work buffers (for the temp buffer offset).
-void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, size_t tmp_tf0,
-             uint64_t stream_tf, cudaStream_t s, uint32_t &launches)
+// Radix schedule of a Stockham FFT of size n with radices from {16, 8, 4, 2, 5, 3, 7}.
+bool fft_radices(int n, std::vector<unsigned char> &rad)
+{
+    rad.clear();
+    if (n < 2) return false;
+    while (n % 16 == 0) { rad.push_back(16); n /= 16; }
+    while (n % 8 == 0) { rad.push_back(8); n /= 8; }
+    while (n % 4 == 0) { rad.push_back(4); n /= 4; }
+    while (n % 2 == 0) { rad.push_back(2); n /= 2; }
+    for (int f : {5, 3, 7})
+        while (n % f == 0) { rad.push_back((unsigned char)f); n /= f; }
+    return n == 1 && rad.size() <= (size_t)RES_MAX_PASSES;
+}
+
+// symbols [-> FIR]: d_bits -> dst (float2 stream, or the final format when `last`)
+void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst, bool last, size_t tmp_tf0,
+                   uint64_t stream_tf, cudaStream_t s, uint32_t &launches)
 {
     const ModeInfo &m = h->m;
     const dabmod_b200_config &c = h->cfg;
     const bool fir = h->has_fir();
-    const bool post = h->has_post();
+    const bool post = last && h->has_post();
 
     SymParams sp{};
     sp.L = m.L; sp.K = m.K; sp.N = m.N;
@@ -305,11 +334,11 @@ void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, si
     sp.bits = d_bits;
     sp.tf_offset = stream_tf;
     const bool sym_last = !fir;
-    sp.out = sym_last ? d_out : (void *)(h->d_tmp.p + tmp_tf0 * (size_t)m.tf_samples);
-    sp.post = make_post(h, sym_last && post);
+    sp.out = sym_last ? dst : (void *)(h->d_tmp.p + tmp_tf0 * (size_t)m.tf_samples);
+    const bool sym_post = sym_last && post;
+    sp.post = make_post(h, sym_post);
 
     const int grid = (int)(n_tf * sp.n_chunks);
-    const bool sym_post = sym_last && post;
     ProfScope prof_sym(h, "k_symbols", s);
     switch (m.N) {
         case 2048: launch_symbols_n<2048>(sp, sym_post, grid, s); break;
@@ -324,7 +353,7 @@ void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, si
     if (fir) {
         FirParams fp{};
         fp.in = reinterpret_cast<const float2 *>(sp.out);
-        fp.out = d_out;
+        fp.out = dst;
         fp.tf_samples = m.tf_samples;
         fp.tiles_per_tf = (m.tf_samples + FIR_TILE - 1) / FIR_TILE;
         std::memset(fp.taps, 0, sizeof(fp.taps));
@@ -338,6 +367,62 @@ void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, si
         prof_fir.end();
         launches++;
     }
+}
+
+// Resampler over n_tf TFs of the stream: in (float2, n_tf*tf_samples) -> d_out
+void enqueue_resampler(dabmod_b200 *h, const float2 *in, size_t n_tf, void *d_out, cudaStream_t s,
+                       uint32_t &launches)
+{
+    const ResamplerPlan &rp = h->rp;
+    const bool post = h->has_post();
+    ResParams p{};
+    p.ni = rp.ni; p.no = rp.no;
+    p.total_hops = (long long)(n_tf * (size_t)h->m.tf_samples / (size_t)(rp.ni / 2));
+    p.factor = rp.factor;
+    p.in = in;
+    p.hist = h->d_hist.p;
+    p.win = h->d_res_win.p;
+    p.tw_in = h->d_tw_in.p;
+    p.tw_out = h->d_tw_out.p;
+    p.n_rad_in = (int)h->rad_in.size();
+    p.n_rad_out = (int)h->rad_out.size();
+    std::memcpy(p.rad_in, h->rad_in.data(), h->rad_in.size());
+    std::memcpy(p.rad_out, h->rad_out.data(), h->rad_out.size());
+    p.scratch = h->res_smem ? nullptr : h->d_scratch.p;
+    p.out = d_out;
+    p.post = make_post(h, post);
+    const int grid = (int)std::min<long long>(p.total_hops, h->res_grid);
+    ProfScope prof(h, "k_resample", s);
+    if (post) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_resample_generic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)h->res_smem));
+        k_resample_generic<true><<<grid, RESG_THREADS, h->res_smem, s>>>(p);
+    }
+    else {
+        CUDA_CHECK(cudaFuncSetAttribute(k_resample_generic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)h->res_smem));
+        k_resample_generic<false><<<grid, RESG_THREADS, h->res_smem, s>>>(p);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    prof.end();
+    launches++;
+    // stream state for the next launch: the last Ni input samples (Resampler.cpp:143-145,185-191)
+    const size_t total = n_tf * (size_t)h->m.tf_samples;
+    CUDA_CHECK(cudaMemcpyAsync(h->d_hist.p, in + total - rp.ni, sizeof(float2) * rp.ni, cudaMemcpyDeviceToDevice, s));
+}
+
+// Enqueue the kernel family for n_tf TFs: d_bits -> d_out.  `tmp_tf0` = index of
+// the first TF within the handle's work buffers (for the temp buffer offsets).
+void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, size_t tmp_tf0,
+             uint64_t stream_tf, cudaStream_t s, uint32_t &launches)
+{
+    if (!h->has_res) {
+        enqueue_front(h, d_bits, n_tf, d_out, true, tmp_tf0, stream_tf, s, launches);
+        return;
+    }
+    float2 *front = (h->has_fir() ? h->d_tmp2.p : h->d_tmp.p) + tmp_tf0 * (size_t)h->m.tf_samples;
+    enqueue_front(h, d_bits, n_tf, front, false, tmp_tf0, stream_tf, s, launches);
+    enqueue_resampler(h, front, n_tf, d_out, s, launches);
 }
 
 void validate_config(const dabmod_b200_config &c)
@@ -356,8 +441,6 @@ void validate_config(const dabmod_b200_config &c)
     if (c.window_overlap > 0)
         throw ApiError(DABMOD_B200_EUNSUPPORTED, "OFDM windowing is not implemented yet");
     if (c.cfr_enable) throw ApiError(DABMOD_B200_EUNSUPPORTED, "CFR is not implemented yet");
-    if (c.output_rate && c.output_rate != 2048000)
-        throw ApiError(DABMOD_B200_EUNSUPPORTED, "Resampler is not implemented yet");
     if (c.max_batch < 0) throw ApiError(DABMOD_B200_EINVAL, "max_batch < 0");
 }
 
@@ -455,9 +538,45 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
         build_tables(h);
 
         const size_t nb = (size_t)h->cfg.max_batch;
+        if (h->cfg.output_rate != 2048000) {
+            // DabModulator.cpp:260-268: Resampler(2048000, outputRate, spacing)
+            const ResamplerPlan rp = resampler_plan(2048000, h->cfg.output_rate, h->m.N);
+            if (rp.ni < 4 || rp.no < 2 || h->m.tf_samples % (rp.ni / 2) != 0)
+                throw ApiError(DABMOD_B200_EUNSUPPORTED,
+                               "Resampler: FFT sizes " + std::to_string(rp.ni) + "/" + std::to_string(rp.no) +
+                                   " do not tile the transmission frame (the reference reads out of bounds here)");
+            if (!fft_radices(rp.ni, h->rad_in) || !fft_radices(rp.no, h->rad_out))
+                throw ApiError(DABMOD_B200_EUNSUPPORTED,
+                               "Resampler: FFT size " + std::to_string(rp.no) + " has a prime factor above 7");
+            h->rp = rp;
+            h->has_res = true;
+            h->d_res_win.upload(resampler_window(rp.ni), h->s_compute);
+            std::vector<float> t;
+            twiddle_table(rp.ni, t);
+            h->d_tw_in.alloc(rp.ni);
+            CUDA_CHECK(cudaMemcpyAsync(h->d_tw_in.p, t.data(), sizeof(float2) * rp.ni, cudaMemcpyHostToDevice, h->s_compute));
+            twiddle_table(rp.no, t);
+            h->d_tw_out.alloc(rp.no);
+            CUDA_CHECK(cudaMemcpyAsync(h->d_tw_out.p, t.data(), sizeof(float2) * rp.no, cudaMemcpyHostToDevice, h->s_compute));
+            CUDA_CHECK(cudaStreamSynchronize(h->s_compute));   // `t` is reused / goes out of scope
+            h->d_hist.alloc(rp.ni);
+            CUDA_CHECK(cudaMemsetAsync(h->d_hist.p, 0, sizeof(float2) * rp.ni, h->s_compute));
+            const size_t nmax = (size_t)std::max(rp.ni, rp.no);
+            const size_t need = 2 * nmax * sizeof(float2);
+            if (need <= 96 * 1024) {
+                h->res_smem = need;
+                h->res_grid = h->sm_count * 2;
+            }
+            else {
+                h->res_smem = 0;
+                h->res_grid = h->sm_count * 2;
+                h->d_scratch.alloc((size_t)h->res_grid * 2 * nmax);
+            }
+        }
         h->d_bits.alloc(nb * h->m.tf_in_bytes);
         h->d_out.alloc(nb * h->out_bytes_per_tf());
-        h->d_tmp.alloc(nb * (size_t)h->m.tf_samples);
+        if (h->has_fir() || h->has_res) h->d_tmp.alloc(nb * (size_t)h->m.tf_samples);
+        if (h->has_fir() && h->has_res) h->d_tmp2.alloc(nb * (size_t)h->m.tf_samples);
         CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
         *out = h;
     });
@@ -597,6 +716,11 @@ int dabmod_b200_reset(dabmod_b200 *h)
         if (!h) throw ApiError(DABMOD_B200_EINVAL, "null handle");
         std::lock_guard<std::mutex> lock(h->mtx);
         h->tf_counter = 0;
+        if (h->has_res) {
+            CUDA_CHECK(cudaSetDevice(h->device));
+            CUDA_CHECK(cudaMemsetAsync(h->d_hist.p, 0, sizeof(float2) * h->rp.ni, h->s_compute));
+            CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+        }
     });
 }
 
@@ -604,9 +728,27 @@ int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits
 {
     return guard([&] {
         if (!h) throw ApiError(DABMOD_B200_EINVAL, "null handle");
-        (void)prev_bits; (void)nbytes;
         std::lock_guard<std::mutex> lock(h->mtx);
         h->tf_counter = tf_index;
+        if (!h->has_res) return;
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (h->tables_dirty) build_tables(h);
+        cudaStream_t s = h->s_compute;
+        if (!prev_bits || tf_index == 0) {
+            CUDA_CHECK(cudaMemsetAsync(h->d_hist.p, 0, sizeof(float2) * h->rp.ni, s));
+        }
+        else {
+            // re-run TF tf_index-1 up to the resampler input; keep its last Ni samples
+            if (nbytes != (size_t)h->m.tf_in_bytes)
+                throw ApiError(DABMOD_B200_EINVAL, "seek: prev_bits must be one TF block");
+            CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p, prev_bits, nbytes, cudaMemcpyHostToDevice, s));
+            float2 *front = h->has_fir() ? h->d_tmp2.p : h->d_tmp.p;
+            uint32_t launches = 0;
+            enqueue_front(h, h->d_bits.p, 1, front, false, 0, tf_index - 1, s, launches);
+            CUDA_CHECK(cudaMemcpyAsync(h->d_hist.p, front + h->m.tf_samples - h->rp.ni, sizeof(float2) * h->rp.ni,
+                                       cudaMemcpyDeviceToDevice, s));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(s));
     });
 }
 

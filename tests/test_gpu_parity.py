@@ -100,3 +100,151 @@ def test_errors(dm, rng):
         mod.set_param("nonexistent", "1")
     # empty batch is a no-op
     assert mod.process_batch(np.zeros((0, mod.tf_in_bytes), np.uint8)).size == 0
+
+
+# ---------------------------------------------------------------------------
+# Resampler (Resampler.cpp:131-195): FFT overlap-add with state across TFs
+# ---------------------------------------------------------------------------
+RES_CASES = [(1, 8192000), (1, 10000000), (2, 4096000), (1, 1536000), (4, 2500000), (3, 2400000), (2, 3200000)]
+
+
+@pytest.mark.parametrize("mode,rate", RES_CASES)
+def test_resampler_batch(dm, rng, mode, rate):
+    """BASELINE configs 3/5 geometry: FIR + resampler, 3 TFs of one stream in one call."""
+    bits = bits_for(rng, mode, 3)
+    taps = oracle.fir_default_taps()
+    ora = oracle.OracleChain(mode=mode, output_rate=rate, fir_taps=taps).run(bits)
+    mod = dm.Modulator(mode=mode, output_rate=rate, fir_taps=taps, max_batch=3)
+    out = mod.process_batch(bits)
+    assert out.shape[1] == ora[0].size
+    for i in range(3):
+        assert rel_rms(out[i], ora[i]) < TOL, i
+
+
+@pytest.mark.parametrize("mode,rate", [(1, 8192000), (2, 2500000)])
+def test_resampler_state_across_calls(dm, rng, mode, rate):
+    """The overlap buffers persist across process() calls (Resampler.cpp:143-145,185-191)."""
+    bits = bits_for(rng, mode, 4)
+    ora = oracle.OracleChain(mode=mode, output_rate=rate).run(bits)
+    mod = dm.Modulator(mode=mode, output_rate=rate, max_batch=2)
+    got = [mod.process(bits[0]), mod.process(bits[1])] + list(mod.process_batch(bits[2:]))
+    for i in range(4):
+        assert rel_rms(got[i], ora[i]) < TOL, i
+    # reset() forgets the history: TF 0 again reproduces the first output bit for bit
+    mod.reset()
+    again = mod.process(bits[0])
+    assert np.array_equal(again.view(np.uint32), got[0].view(np.uint32))
+    # seek(): a second handle (another GPU in the sharded run) picks the stream up at TF 2
+    mod2 = dm.Modulator(mode=mode, output_rate=rate, max_batch=2)
+    mod2.seek(2, bits[1])
+    tail = mod2.process_batch(bits[2:])
+    for i in range(2):
+        assert rel_rms(tail[i], ora[2 + i]) < TOL, i
+
+
+def test_resampler_unsupported_rate(dm):
+    with pytest.raises(dm.DabModError):
+        dm.Modulator(mode=1, output_rate=2048001)
+
+
+# ---------------------------------------------------------------------------
+# MemlessPoly / FormatConverter epilogues, TII, CicEqualizer
+# ---------------------------------------------------------------------------
+POLY_AM = [1.0, 0.12, -0.3, 0.05, 0.01]
+POLY_PM = [0.02, -0.4, 0.3, 0.1, -0.05]
+
+
+@pytest.mark.parametrize("chain", ["sym", "fir", "res"])
+def test_memless_poly(dm, rng, chain):
+    kw = dict(mode=2, normalise=1.0 / 46000.0, poly=POLY_AM + POLY_PM)
+    if chain != "sym":
+        kw["fir_taps"] = oracle.fir_default_taps()
+    if chain == "res":
+        kw["output_rate"] = 4096000
+    bits = bits_for(rng, 2, 2)
+    ora = oracle.OracleChain(**kw).run(bits)
+    out = dm.Modulator(max_batch=2, **kw).process_batch(bits)
+    for i in range(2):
+        assert rel_rms(out[i], ora[i]) < TOL
+
+
+def test_memless_lut(dm, rng):
+    lut = (1.0 + 0.1 * rng.standard_normal(32)).astype(np.float32)
+    scale = np.float32(2 ** 32 / 1.5)
+    kw = dict(mode=2, normalise=1.0 / 46000.0, lut=(scale, lut))
+    bits = bits_for(rng, 2, 2)
+    ora = oracle.OracleChain(**kw).run(bits)
+    out = dm.Modulator(max_batch=2, **kw).process_batch(bits)
+    for i in range(2):
+        # a magnitude within float rounding of a LUT bin edge may pick the neighbouring entry
+        bad = np.abs(out[i] - ora[i]) > 1e-5 * np.abs(ora[i]).max()
+        assert bad.sum() <= 4
+
+
+@pytest.mark.parametrize("fmt,dg", [("s16", 0.8), ("s16", 3.0), ("u8", 0.003), ("s8", 0.003), ("s8", 0.02)])
+@pytest.mark.parametrize("chain", ["sym", "fir", "res"])
+def test_format_converter(dm, rng, fmt, dg, chain):
+    kw = dict(mode=2, digital_gain=dg, fmt=fmt)
+    if chain != "sym":
+        kw["fir_taps"] = oracle.fir_default_taps()
+    if chain == "res":
+        kw["output_rate"] = 4096000
+    bits = bits_for(rng, 2, 1)
+    och = oracle.OracleChain(**kw)
+    ora = och.run(bits)[0].astype(np.int32)
+    mod = dm.Modulator(**kw)
+    out = mod.process_batch(bits)[0].astype(np.int32)
+    assert out.size == ora.size
+    # float32 inputs differ by ~2e-7 relative: a value next to an integer boundary may truncate to
+    # the neighbour.  P(mismatch) = |delta| in LSBs <= 2e-7 * 32767 = 0.0065 per component.
+    assert np.abs(out - ora).max() <= 1
+    assert np.count_nonzero(out != ora) < 0.01 * ora.size
+    # clipped-sample counter (FormatConverter.cpp:176)
+    assert abs(int(mod.num_clipped_samples) - int(och.clipped)) <= max(4, 0.002 * och.clipped)
+
+
+@pytest.mark.parametrize("mode,comb,pattern,old", [(1, 1, 11, 0), (1, 23, 69, 1), (2, 4, 0, 0), (2, 23, 35, 1)])
+def test_tii(dm, rng, mode, comb, pattern, old):
+    bits = bits_for(rng, mode, 4)
+    tii = (comb, pattern, old)
+    ora = oracle.OracleChain(mode=mode, tii=tii).run(bits)
+    mod = dm.Modulator(mode=mode, tii=tii, max_batch=4)
+    out = mod.process_batch(bits)
+    null = oracle.mode_params(mode).null_size
+    for i in range(4):
+        assert rel_rms(out[i], ora[i]) < TOL
+        # inserted on every second TF starting with the first (TII.cpp:225-242)
+        assert (np.abs(out[i][:null]).max() > 0) == (i % 2 == 0)
+    # one TF per call keeps the same parity sequence
+    mod.reset()
+    for i in range(3):
+        assert rel_rms(mod.process(bits[i]), ora[i]) < TOL
+
+
+def test_tii_modes_without_tii(dm, rng):
+    """TM III/IV: the reference's TII constructor throws and NullSymbol is used (DabModulator.cpp:178-190)."""
+    bits = bits_for(rng, 4, 1)
+    ora = oracle.OracleChain(mode=4).run(bits)
+    out = dm.Modulator(mode=4, tii=(1, 1)).process_batch(bits)
+    assert rel_rms(out[0], ora[0]) < TOL
+
+
+@pytest.mark.parametrize("clock", [32768000, 400000000, 100000000])
+def test_cic_equalizer(dm, rng, clock):
+    bits = bits_for(rng, 1, 1)
+    ora = oracle.OracleChain(mode=1, clock_rate=clock).run(bits)
+    out = dm.Modulator(mode=1, clock_rate=clock).process_batch(bits)
+    assert rel_rms(out[0], ora[0]) < TOL
+
+
+def test_full_chain_c3_c5(dm, rng):
+    """BASELINE configs 3 and 5: FIR + resampler (8.192 / 10 Msps) + MemlessPoly, normalised."""
+    bits = bits_for(rng, 1, 2)
+    am = [1.0, 0.05, -0.02, 0.0, 0.0]
+    pm = [0.0, 0.1, -0.05, 0.0, 0.0]
+    for rate in (8192000, 10000000):
+        kw = dict(mode=1, output_rate=rate, normalise=1.0 / 46000.0, fir_taps=oracle.fir_default_taps(), poly=am + pm)
+        ora = oracle.OracleChain(**kw).run(bits)
+        out = dm.Modulator(max_batch=2, **kw).process_batch(bits)
+        for i in range(2):
+            assert rel_rms(out[i], ora[i]) < TOL
