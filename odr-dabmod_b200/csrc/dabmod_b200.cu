@@ -100,7 +100,8 @@ struct dabmod_b200 {
     DevBuf<uint16_t> d_bin_of_src;
     DevBuf<uint8_t> d_phase0;
     DevBuf<float> d_cic;
-    DevBuf<float> d_twiddle;       // interleaved re/im, 2048 entries
+    DevBuf<float> d_twiddle;       // interleaved re/im, per-pass tables (symbol_fft_twiddles)
+    int n_twiddle = 0;
     DevBuf<uint16_t> d_tii_bin;
     DevBuf<float> d_tii_val;
     DevBuf<float> d_window;
@@ -251,10 +252,9 @@ void launch_fir_p(const FirParams &p, int ntaps, int grid, cudaStream_t s)
 {
     if (ntaps <= 16) k_fir<16, POST><<<grid, FIR_THREADS, 0, s>>>(p);
     else if (ntaps <= 32) k_fir<32, POST><<<grid, FIR_THREADS, 0, s>>>(p);
-    else if (ntaps <= 48) k_fir<48, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+    else if (ntaps <= 45) k_fir<45, POST><<<grid, FIR_THREADS, 0, s>>>(p);   // the reference's default filter
     else if (ntaps <= 64) k_fir<64, POST><<<grid, FIR_THREADS, 0, s>>>(p);
-    else if (ntaps <= 96) k_fir<96, POST><<<grid, FIR_THREADS, 0, s>>>(p);
-    else k_fir<128, POST><<<grid, FIR_THREADS, 0, s>>>(p);
+    else k_fir<0, POST><<<grid, FIR_THREADS, 0, s>>>(p);                     // any length, chunked tap loop
 }
 
 struct ProfScope {
@@ -319,6 +319,7 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     sp.phase0 = h->d_phase0.p;
     sp.cic = h->use_cic ? h->d_cic.p : nullptr;
     sp.twiddle = reinterpret_cast<const float2 *>(h->d_twiddle.p);
+    sp.n_twiddle = h->n_twiddle;
     sp.tii_count = h->tii_count;
     sp.tii_parity = 0;
     sp.tii_bin = h->d_tii_bin.p;
@@ -356,8 +357,9 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         fp.out = dst;
         fp.tf_samples = m.tf_samples;
         fp.tiles_per_tf = (m.tf_samples + FIR_TILE - 1) / FIR_TILE;
+        fp.ntaps = (int)h->fir_taps.size();
         std::memset(fp.taps, 0, sizeof(fp.taps));
-        std::memcpy(fp.taps, h->fir_taps.data(), h->fir_taps.size() * sizeof(float));
+        for (size_t j = 0; j < h->fir_taps.size(); j++) fp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
         fp.post = make_post(h, post);
         const int fgrid = (int)(n_tf * fp.tiles_per_tf);
         ProfScope prof_fir(h, "k_fir", s);
@@ -530,9 +532,11 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
 
+        h->m = mode_info(h->cfg.mode);
         std::vector<float> tw;
-        twiddle_table(SYM_POINTS, tw);
+        symbol_fft_twiddles(h->m.N, tw);
         h->d_twiddle.upload(tw, h->s_compute);
+        h->n_twiddle = (int)(tw.size() / 2);
         h->d_clipped.alloc(1);
         CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
         build_tables(h);

@@ -124,7 +124,9 @@ __device__ __host__ __forceinline__ constexpr int spad(int i) { return i + (i >>
 // One Stockham radix-R pass over `nfft` independent transforms of size N that
 // lie back to back in `buf` (element i of transform g at spad(g*N + i)).
 //   Ns   = product of the radices of the passes already done
-//   tw   = table of e^{+j 2 pi k / NT}, k in [0, NT), NT a multiple of Ns*R
+//   twp  = this pass's twiddles, twp[(r-1)*Ns + k] = e^{+j 2 pi k r / (Ns*R)},
+//          r in [1, R), k in [0, Ns): consecutive lanes read consecutive k, so
+//          the reads are bank-conflict free (unused when Ns == 1)
 // The pass is split in two halves so that the caller can put ONE barrier
 // between "everyone has read" and "everyone writes" (in-place operation).
 // Each thread owns PER = (nfft*N/R)/NTHREADS butterflies.
@@ -133,10 +135,9 @@ struct StockhamPass {
     float2 v[PER][R];
 
     __device__ __forceinline__ void load(const float2 *buf, int tid, int nthreads, int N, int Ns,
-                                         const float2 *tw, int NT)
+                                         const float2 *twp)
     {
         const int nb = N / R; // butterflies per transform
-        const int twstep = NT / (Ns * R);
 #pragma unroll
         for (int p = 0; p < PER; p++) {
             const int b = tid + p * nthreads;
@@ -147,7 +148,7 @@ struct StockhamPass {
             for (int r = 0; r < R; r++) v[p][r] = buf[spad(base + r * nb)];
             if (Ns > 1) {
 #pragma unroll
-                for (int r = 1; r < R; r++) v[p][r] = cmul(v[p][r], tw_dir<INV>(tw[k * r * twstep]));
+                for (int r = 1; r < R; r++) v[p][r] = cmul(v[p][r], tw_dir<INV>(twp[(r - 1) * Ns + k]));
             }
             fft_radix<R, INV>(v[p]);
         }

@@ -145,7 +145,8 @@ struct SymParams {
     const uint16_t *bin_of_src;   // K: FFT bin of the carrier that source j is interleaved to
     const uint8_t *phase0;        // K: phase reference of that carrier, units of pi/4 (even)
     const float *cic;             // K or nullptr: CicEqualizer gain of that carrier
-    const float2 *twiddle;        // 2048 entries e^{+j 2 pi k / 2048}
+    const float2 *twiddle;        // per-pass tables of the mode's IFFT (tables.h: symbol_fft_twiddles)
+    int n_twiddle;
     // null symbol / TII
     int tii_count;                // carriers set in the TII symbol (0 = plain null symbol)
     int tii_parity;               // TII is inserted on TFs where ((tf + tii_parity) & 1) == 0
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
     const bool tii_on = p.tii_count > 0 && (((p.tf_offset + tf + p.tii_parity) & 1) == 0);
 
     // ---- per-CTA tables ----
-    for (int i = tid; i < SYM_POINTS; i += SYM_THREADS) sm.tw[i] = __ldg(p.twiddle + i);
+    for (int i = tid; i < p.n_twiddle; i += SYM_THREADS) sm.tw[i] = __ldg(p.twiddle + i);
     for (int b = tid; b < 256; b += SYM_THREADS) {
         uint32_t s = 0;
 #pragma unroll
@@ -321,43 +322,49 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
         if (grp == 0 && tii_on) __syncthreads();
 
         // ---- 2. inverse FFT of the G symbols, in place ----
-        if (N == 2048) {
-            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
-            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 256, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 256); __syncthreads(); }
-        }
-        else if (N == 1024) {
-            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
-            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 128, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 128); __syncthreads(); }
-        }
-        else if (N == 512) {
-            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 8, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 8); __syncthreads(); }
-            { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 64, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 64); __syncthreads(); }
-        }
-        else {
-            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw, SYM_POINTS);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
-        }
-
+        // Per-pass twiddle tables (see StockhamPass): pass 2 at sm.tw, pass 3 behind it.
         // ---- 3. gain: statistics per symbol over its N samples ----
         // thread (eg, tt): symbol eg of the group, samples tt + TG*i
         const int eg = tid / TG, tt = tid - eg * TG;
         float2 x[16];
+        if (N == 2048) {
+            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw);
+              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
+            // last pass stays in registers: butterfly p of this thread yields samples
+            // tid + 128*p + 256*r, i.e. x[2r + p] of the emit layout (TG = 128)
+            StockhamPass<8, true, 2> ps;
+            ps.load(sm.buf, tid, SYM_THREADS, N, 256, sm.tw + 15 * 16);
 #pragma unroll
-        for (int i = 0; i < 16; i++) x[i] = sm.buf[spad(eg * N + tt + TG * i)];
+            for (int r = 0; r < 8; r++) { x[2 * r] = ps.v[0][r]; x[2 * r + 1] = ps.v[1][r]; }
+        }
+        else {
+            if (N == 1024) {
+                { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
+                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 128, sm.tw + 7 * 16);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 128); __syncthreads(); }
+            }
+            else if (N == 512) {
+                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 8, sm.tw);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 8); __syncthreads(); }
+                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 64, sm.tw + 7 * 8);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 64); __syncthreads(); }
+            }
+            else {
+                { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
+                { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw);
+                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = sm.buf[spad(eg * N + tt + TG * i)];
+        }
         float g_sym;
         if (p.gain_mode == 0) {
             g_sym = 512.0f;
@@ -476,13 +483,14 @@ namespace dabmod {
 //
 // One CTA = one tile of FIR_TILE consecutive samples of one TF.  The tile and
 // its NT-1 sample forward halo are staged in shared memory; each thread keeps
-// FIR_M consecutive outputs in registers and slides over FIR_M+NT-1 inputs, so
-// every input is read from shared memory once per thread and every tap is an
-// immediate constant-bank operand of the FMA.  Accumulation runs in ascending
+// FIR_M consecutive outputs in registers (packed I/Q pairs) and slides over
+// FIR_M+NT-1 inputs, so every input is read from shared memory once per thread
+// ((FIR_M+NT-1)/FIR_M loads per output) and every (tap, tap) pair is a uniform-
+// register operand of one FFMA2.  Accumulation runs in ascending
 // tap order like the reference's inner loop.
 // ---------------------------------------------------------------------------
-constexpr int FIR_THREADS = 256;
-constexpr int FIR_M = 8;
+constexpr int FIR_THREADS = 128;
+constexpr int FIR_M = 16;
 constexpr int FIR_TILE = FIR_THREADS * FIR_M;
 
 struct FirParams {
@@ -490,26 +498,41 @@ struct FirParams {
     void *out;
     int tf_samples;
     int tiles_per_tf;
-    float taps[MAX_FIR_TAPS];   // zero padded to the template's NT
+    int ntaps;
+    float2 taps[MAX_FIR_TAPS];  // (tap, tap) pairs, zero padded
     PostParams post;
 };
 
-// shared-memory index padding for 8-byte elements read with a stride of FIR_M
-__device__ __forceinline__ constexpr int fpad(int i) { return i + (i >> 3); }
+// Blackwell packed FP32 (sm_100 __ffma2_rn -> SASS FFMA2): one instruction does the
+// I and the Q multiply-accumulate of a tap (same rounding as two fmaf), halving
+// the issue slots of the FIR inner loop.
+// shared-memory index padding for 8-byte elements read with a lane stride of FIR_M:
+// thread t starts at 17*t, an odd stride, so a half-warp covers all 16 bank pairs
+static_assert(FIR_M == 16, "fpad assumes FIR_M == 16");
+__device__ __forceinline__ constexpr int fpad(int i) { return i + (i >> 4); }
+
+// NT > 0: tap count known at compile time, tap loop fully unrolled (each input is
+// loaded once per thread).  NT == 0: any tap count up to MAX_FIR_TAPS, taps consumed
+// in chunks of FIR_CHUNK with the chunk body unrolled.
+constexpr int FIR_CHUNK = 16;
 
 template <int NT, bool POST>
 __global__ void __launch_bounds__(FIR_THREADS) k_fir(const __grid_constant__ FirParams p)
 {
-    constexpr int SPAN = FIR_TILE + NT;      // samples staged (one spare keeps SPAN even)
-    __shared__ float2 xs[SPAN + SPAN / 8 + 8];
+    constexpr int NTMAX = NT > 0 ? NT : MAX_FIR_TAPS;
+    constexpr int SPAN = FIR_TILE + NTMAX;      // samples staged (>= tile + halo, kept even)
+    constexpr int XS_IN = SPAN + SPAN / 16 + 8;            // padded input window
+    constexpr int XS_OUT = FIR_THREADS * (FIR_M + 2);      // padded output staging (float4 slots 9*t)
+    __shared__ __align__(16) float2 xs[XS_IN > XS_OUT ? XS_IN : XS_OUT];
     const int tid = threadIdx.x;
     const int tf = blockIdx.x / p.tiles_per_tf;
     const int tile = blockIdx.x - tf * p.tiles_per_tf;
     const int n0 = tile * FIR_TILE;
     const float2 *in = p.in + (size_t)tf * p.tf_samples;
+    const int span = NT > 0 ? SPAN : FIR_TILE + ((p.ntaps + FIR_CHUNK - 1) / FIR_CHUNK) * FIR_CHUNK;
 
     // stage: two samples (16 B) per thread per step, zero beyond the TF end
-    for (int i = 2 * tid; i < SPAN; i += 2 * FIR_THREADS) {
+    for (int i = 2 * tid; i < span; i += 2 * FIR_THREADS) {
         const int n = n0 + i;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (n + 1 < p.tf_samples) {
@@ -527,33 +550,57 @@ __global__ void __launch_bounds__(FIR_THREADS) k_fir(const __grid_constant__ Fir
     float2 acc[FIR_M];
 #pragma unroll
     for (int m = 0; m < FIR_M; m++) acc[m] = make_float2(0.f, 0.f);
-    const float2 *x = xs + tid * (FIR_M + 1);    // fpad(tid * FIR_M) with FIR_M == 8
+    if (NT > 0) {
+        const float2 *x = xs + tid * (FIR_M + 1);    // fpad(tid * FIR_M)
 #pragma unroll
-    for (int i = 0; i < FIR_M + NT - 1; i++) {
-        const float2 v = x[i + (i >> 3)];
+        for (int i = 0; i < FIR_M + NTMAX - 1; i++) {
+            const float2 v = x[i + (i >> 4)];
 #pragma unroll
-        for (int m = 0; m < FIR_M; m++) {
-            const int j = i - m;
-            if (j >= 0 && j < NT) {
-                acc[m].x = fmaf(v.x, p.taps[j], acc[m].x);
-                acc[m].y = fmaf(v.y, p.taps[j], acc[m].y);
+            for (int m = 0; m < FIR_M; m++) {
+                const int j = i - m;
+                if (j >= 0 && j < NTMAX) acc[m] = __ffma2_rn(v, p.taps[j], acc[m]);
             }
         }
     }
+    else {
+        // ascending tap order is kept: chunk c covers taps [16c, 16c+16)
+        for (int c = 0; c * FIR_CHUNK < p.ntaps; c++) {
+            const int i0 = tid * FIR_M + c * FIR_CHUNK;
+#pragma unroll
+            for (int i = 0; i < FIR_M + FIR_CHUNK - 1; i++) {
+                const float2 v = xs[fpad(i0 + i)];
+#pragma unroll
+                for (int m = 0; m < FIR_M; m++) {
+                    const int j = i - m;
+                    if (j >= 0 && j < FIR_CHUNK) acc[m] = __ffma2_rn(v, p.taps[c * FIR_CHUNK + j], acc[m]);
+                }
+            }
+        }
+    }
+    // Transpose through shared memory so that the global stores are coalesced:
+    // thread t parks its FIR_M outputs at 16-byte slots 9*t + m/2 (odd slot stride:
+    // conflict-free float4 writes), then the CTA streams the tile out in order.
+    __syncthreads();
+    float4 *ys = reinterpret_cast<float4 *>(xs);
+#pragma unroll
+    for (int m = 0; m < FIR_M; m += 2)
+        ys[tid * (FIR_M / 2 + 1) + m / 2] = make_float4(acc[m].x, acc[m].y, acc[m + 1].x, acc[m + 1].y);
+    __syncthreads();
 
     unsigned clip = 0;
-    const int nbase = n0 + tid * FIR_M;
-    const size_t obase = (size_t)tf * p.tf_samples + nbase;
-    if (!POST && nbase + FIR_M <= p.tf_samples) {
-        float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + obase);
+    const size_t obase = (size_t)tf * p.tf_samples + n0;
 #pragma unroll
-        for (int m = 0; m < FIR_M; m += 2)
-            o[m / 2] = make_float4(acc[m].x, acc[m].y, acc[m + 1].x, acc[m + 1].y);
-    }
-    else {
-#pragma unroll
-        for (int m = 0; m < FIR_M; m++)
-            if (nbase + m < p.tf_samples) store_sample<POST>(p.out, obase + m, acc[m], p.post, clip);
+    for (int k = 0; k < FIR_M / 2; k++) {
+        const int q = k * FIR_THREADS + tid;          // pair index within the tile
+        const int n = 2 * q;                          // sample index within the tile
+        const float4 v = ys[q + (q >> 3)];
+        if (!POST && n0 + n + 1 < p.tf_samples) {
+            reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + obase)[q] = v;
+        }
+        else {
+            if (n0 + n < p.tf_samples) store_sample<POST>(p.out, obase + n, make_float2(v.x, v.y), p.post, clip);
+            if (n0 + n + 1 < p.tf_samples) store_sample<POST>(p.out, obase + n + 1, make_float2(v.z, v.w), p.post, clip);
+        }
     }
     if (POST && p.post.format != 0) flush_clip(p.post, clip);
 }

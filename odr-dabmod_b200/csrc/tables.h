@@ -187,6 +187,32 @@ inline void twiddle_table(int n, std::vector<float> &re_im)
     }
 }
 
+// Twiddles of the OFDM IFFT passes in the layout StockhamPass reads:
+// for pass (R, Ns) entry (r-1)*Ns + k = e^{+j 2 pi k r / (Ns R)}; first pass has none.
+// Radix plans: N=2048: 16,16,8; 1024: 16,8,8; 512: 8,8,8; 256: 16,16 (kernels.cuh).
+inline void symbol_fft_twiddles(int N, std::vector<float> &re_im)
+{
+    std::vector<int> rad;
+    switch (N) {
+        case 2048: rad = {16, 16, 8}; break;
+        case 1024: rad = {16, 8, 8}; break;
+        case 512: rad = {8, 8, 8}; break;
+        default: rad = {16, 16}; break;
+    }
+    re_im.clear();
+    int Ns = rad[0];
+    for (size_t i = 1; i < rad.size(); i++) {
+        const int R = rad[i];
+        for (int r = 1; r < R; r++)
+            for (int k = 0; k < Ns; k++) {
+                const double a = 2.0 * M_PI * (double)k * (double)r / ((double)Ns * (double)R);
+                re_im.push_back((float)cos(a));
+                re_im.push_back((float)sin(a));
+            }
+        Ns *= R;
+    }
+}
+
 // Resampler geometry (Resampler.cpp:51-83): L/M after reduction by the gcd, FFT
 // sizes from the `resolution` (= OFDM spacing, DabModulator.cpp:265-268) and the
 // float32 scale factor applied between the two transforms.

@@ -23,12 +23,18 @@ __global__ void __launch_bounds__(256) k(float *out, float s, int iters, const f
             if (MODE == 1) a[i] = fmaf(a[i], cst.x, a[(i + 1) & 15]);   // FFMA reg,const,reg
             if (MODE == 2) a[i] = a[i] + s;                             // FADD
             if (MODE == 5) a[i] = fmaf(a[i], 1.0009765625f, 0.5f);      // FFMA imm
+            if (MODE == 8) { if (i & 1) a[i] = fmaf(a[i], s, 0.5f * s); else a[i] = fminf(a[i], s) ; }  // FFMA + FMNMX
+            if (MODE == 9) { if (i & 1) a[i] = fmaf(a[i], s, 0.5f * s); else a[i] = __int_as_float(__float_as_int(a[i]) ^ (i + it)); }  // FFMA + LOP3
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             if (MODE == 3) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(ps), "l"(pc));
             if (MODE == 4) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(ps));
             if (MODE == 6) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(ps));
+            if (MODE == 7) {   // alternate FFMA2 / FADD2 on independent chains
+                if (i & 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(ps), "l"(pc));
+                else asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(ps));
+            }
         }
     }
     float r = 0;
@@ -74,5 +80,8 @@ int main()
     run<3>("FFMA2 (f32x2)", 4, 8);
     run<4>("FADD2 (f32x2)", 2, 8);
     run<6>("FMUL2 (f32x2)", 2, 8);
+    run<7>("FFMA2+FADD2 alternating", 3, 8);
+    run<8>("FFMA+FMNMX alternating", 1, 16);
+    run<9>("FFMA+LOP3 alternating", 1, 16);
     return 0;
 }
