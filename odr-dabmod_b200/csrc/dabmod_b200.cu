@@ -95,6 +95,7 @@ struct dabmod_b200 {
     bool tii_supported = false;
     uint64_t tf_counter = 0;       // TFs processed since create/reset (TII parity)
     bool tables_dirty = true;
+    int force_chunks = 0;          // test/tuning knob: CTAs per TF in k_symbols (0 = automatic)
 
     // device tables
     DevBuf<uint16_t> d_bin_of_src;
@@ -233,17 +234,24 @@ PostParams make_post(dabmod_b200 *h, bool enabled)
     return pp;
 }
 
-template <int N>
-void launch_symbols_n(const SymParams &p, bool post, int grid, cudaStream_t s)
+template <int N, bool POST, bool OPT>
+void launch_symbols_npo(const SymParams &p, int grid, cudaStream_t s)
 {
-    const size_t smem = sizeof(SymSmem);
-    if (post) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_symbols<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_symbols<N, true><<<grid, SYM_THREADS, smem, s>>>(p);
+    const size_t smem = sizeof(SymSmem) + (OPT ? sizeof(SymSmemOpt) : 0);
+    CUDA_CHECK(cudaFuncSetAttribute(k_symbols<N, POST, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_symbols<N, POST, OPT><<<grid, SYM_THREADS, smem, s>>>(p);
+}
+
+template <int N>
+void launch_symbols_n(const SymParams &p, bool post, bool opt, int grid, cudaStream_t s)
+{
+    if (opt) {
+        if (post) launch_symbols_npo<N, true, true>(p, grid, s);
+        else launch_symbols_npo<N, false, true>(p, grid, s);
     }
     else {
-        CUDA_CHECK(cudaFuncSetAttribute(k_symbols<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_symbols<N, false><<<grid, SYM_THREADS, smem, s>>>(p);
+        if (post) launch_symbols_npo<N, true, false>(p, grid, s);
+        else launch_symbols_npo<N, false, false>(p, grid, s);
     }
 }
 
@@ -311,6 +319,7 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         const int target_ctas = h->sm_count * 6 * 4;
         int chunks = (int)std::min<size_t>((size_t)sp.n_groups / 2, std::max<size_t>(1, (target_ctas + n_tf - 1) / n_tf));
         chunks = std::max(1, std::min(chunks, 11));
+        if (h->force_chunks > 0) chunks = std::max(1, std::min(h->force_chunks, sp.n_groups / 2));
         sp.groups_per_chunk = (sp.n_groups + chunks - 1) / chunks;
         if (sp.groups_per_chunk < 2) sp.groups_per_chunk = 2;
         sp.n_chunks = (sp.n_groups + sp.groups_per_chunk - 1) / sp.groups_per_chunk;
@@ -339,13 +348,14 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     const bool sym_post = sym_last && post;
     sp.post = make_post(h, sym_post);
 
+    const bool sym_opt = c.cfr_enable != 0 || c.window_overlap > 0;
     const int grid = (int)(n_tf * sp.n_chunks);
     ProfScope prof_sym(h, "k_symbols", s);
     switch (m.N) {
-        case 2048: launch_symbols_n<2048>(sp, sym_post, grid, s); break;
-        case 1024: launch_symbols_n<1024>(sp, sym_post, grid, s); break;
-        case 512: launch_symbols_n<512>(sp, sym_post, grid, s); break;
-        default: launch_symbols_n<256>(sp, sym_post, grid, s); break;
+        case 2048: launch_symbols_n<2048>(sp, sym_post, sym_opt, grid, s); break;
+        case 1024: launch_symbols_n<1024>(sp, sym_post, sym_opt, grid, s); break;
+        case 512: launch_symbols_n<512>(sp, sym_post, sym_opt, grid, s); break;
+        default: launch_symbols_n<256>(sp, sym_post, sym_opt, grid, s); break;
     }
     CUDA_CHECK(cudaGetLastError());
     prof_sym.end();
@@ -427,6 +437,19 @@ void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, si
     enqueue_resampler(h, front, n_tf, d_out, s, launches);
 }
 
+// GuardIntervalInserter.cpp:149-300 needs windowOverlap <= symSize - spacing (it computes
+// `remaining_prefix_length` as an unsigned difference); the kernel keeps 2W window entries on chip.
+void check_window(int mode, int overlap)
+{
+    if (overlap < 0) throw ApiError(DABMOD_B200_EINVAL, "windowlen must be >= 0");
+    const ModeInfo m = mode_info(mode == 0 ? 1 : mode);
+    if (overlap > m.sym_size - m.N)
+        throw ApiError(DABMOD_B200_EINVAL, "windowlen " + std::to_string(overlap) +
+                                               " exceeds the guard interval of this mode");
+    if (2 * overlap > MAX_WINDOW)
+        throw ApiError(DABMOD_B200_EUNSUPPORTED, "windowlen above " + std::to_string(MAX_WINDOW / 2));
+}
+
 void validate_config(const dabmod_b200_config &c)
 {
     if (c.abi_version != DABMOD_B200_ABI_VERSION)
@@ -439,10 +462,7 @@ void validate_config(const dabmod_b200_config &c)
     if (c.dpd_mode < 0 || c.dpd_mode > 2 || (c.dpd_mode && !c.dpd_coefs))
         throw ApiError(DABMOD_B200_EINVAL, "MemlessPoly: invalid coefficients");
     format_bytes(c.format);
-    if (c.window_overlap < 0) throw ApiError(DABMOD_B200_EINVAL, "windowlen must be >= 0");
-    if (c.window_overlap > 0)
-        throw ApiError(DABMOD_B200_EUNSUPPORTED, "OFDM windowing is not implemented yet");
-    if (c.cfr_enable) throw ApiError(DABMOD_B200_EUNSUPPORTED, "CFR is not implemented yet");
+    check_window(c.mode, c.window_overlap);
     if (c.max_batch < 0) throw ApiError(DABMOD_B200_EINVAL, "max_batch < 0");
 }
 
@@ -771,6 +791,7 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
         try {
             if (n == "digital") { ss >> c.digital_gain; }
             else if (n == "profile") { int v; ss >> v; h->profile = v != 0; }
+            else if (n == "sym_chunks") { int v; ss >> v; h->force_chunks = v < 0 ? 0 : v; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {
                 std::string v; ss >> v;
@@ -780,6 +801,14 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
                 else if (v == "var") c.gain_mode = DABMOD_B200_GAIN_VAR;
                 else throw ApiError(DABMOD_B200_EINVAL, "Gainmode " + v + " unknown (fix|max|var)");
             }
+            else if (n == "windowlen") {
+                int v; ss >> v;
+                check_window(c.mode, v);
+                c.window_overlap = v; h->tables_dirty = true;
+            }
+            else if (n == "cfr") { int v; ss >> v; c.cfr_enable = v != 0; }
+            else if (n == "clip") { ss >> c.cfr_clip; }
+            else if (n == "errorclip") { ss >> c.cfr_errclip; }
             else if (n == "tii.enable") { int v; ss >> v; c.tii_enable = v != 0; h->tables_dirty = true; }
             else if (n == "tii.comb") {
                 int v; ss >> v;

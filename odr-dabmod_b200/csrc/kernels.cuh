@@ -12,7 +12,7 @@ constexpr int SYM_POINTS = 2048;     // G * N for every transmission mode
 constexpr int SYM_BUF = SYM_POINTS + SYM_POINTS / 16;  // padded (spad)
 constexpr int MAX_TII = 64;          // 32 carrier pairs
 constexpr int MAX_FIR_TAPS = 128;
-constexpr int MAX_WINDOW = 256;      // 2 * windowOverlap entries kept on chip
+constexpr int MAX_WINDOW = 1024;     // 2 * windowOverlap entries kept on chip (W <= 512)
 
 // ---------------------------------------------------------------------------
 // Epilogue: [MemlessPoly] -> [FormatConverter] -> store.
@@ -178,6 +178,13 @@ struct SymSmem {
     float gain[8];
 };
 
+// extra shared memory of the OPT variant (CFR and/or OFDM windowing)
+struct SymSmemOpt {
+    float2 ref[SYM_BUF];            // frequency-domain symbols as fed to the IFFT (CFR reference)
+    float2 tail[2][MAX_WINDOW];     // windowed falling edge of the previous symbol, double buffered
+    float win[MAX_WINDOW];          // rising edge, 2W entries
+};
+
 // out-position of symbol s inside the TF
 __device__ __forceinline__ int sym_pos(const SymParams &p, int s)
 {
@@ -190,7 +197,47 @@ __device__ __forceinline__ uint32_t phase_step(const uint32_t *spread, unsigned 
     return 0x11111111u + 2u * spread[ib ^ qb] + 4u * spread[qb];
 }
 
-template <int N, bool POST>
+// One in-place Stockham pass over the 2048-point buffer (G transforms of size N).
+template <int R, bool INV, int PER, int N>
+__device__ __forceinline__ void sym_pass(float2 *buf, int tid, int Ns, const float2 *twp)
+{
+    StockhamPass<R, INV, PER> ps;
+    ps.load(buf, tid, SYM_THREADS, N, Ns, twp);
+    __syncthreads();
+    ps.store(buf, tid, SYM_THREADS, N, Ns);
+    __syncthreads();
+}
+
+// All passes of the mode's transform, in place, natural order in and out.
+// Radix plans: N=2048: 16,16,8; 1024: 16,8,8; 512: 8,8,8; 256: 16,16 (tables.h: symbol_fft_twiddles).
+template <int N, bool INV>
+__device__ __forceinline__ void sym_fft(float2 *buf, const float2 *tw, int tid)
+{
+    if (N == 2048) {
+        sym_pass<16, INV, 1, N>(buf, tid, 1, tw);
+        sym_pass<16, INV, 1, N>(buf, tid, 16, tw);
+        sym_pass<8, INV, 2, N>(buf, tid, 256, tw + 15 * 16);
+    }
+    else if (N == 1024) {
+        sym_pass<16, INV, 1, N>(buf, tid, 1, tw);
+        sym_pass<8, INV, 2, N>(buf, tid, 16, tw);
+        sym_pass<8, INV, 2, N>(buf, tid, 128, tw + 7 * 16);
+    }
+    else if (N == 512) {
+        sym_pass<8, INV, 2, N>(buf, tid, 1, tw);
+        sym_pass<8, INV, 2, N>(buf, tid, 8, tw);
+        sym_pass<8, INV, 2, N>(buf, tid, 64, tw + 7 * 8);
+    }
+    else {
+        sym_pass<16, INV, 1, N>(buf, tid, 1, tw);
+        sym_pass<16, INV, 1, N>(buf, tid, 16, tw);
+    }
+}
+
+// OPT = true adds the optional features of the same reference blocks: crest factor
+// reduction (OfdmGenerator.cpp:310-373) and OFDM windowing (GuardIntervalInserter.cpp:149-300).
+// They cost shared memory and registers, so the plain configurations get their own instantiation.
+template <int N, bool POST, bool OPT>
 __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__ SymParams p)
 {
     constexpr int G = SYM_POINTS / N;         // symbols per group
@@ -198,6 +245,7 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
     constexpr int K16 = (N * 3 / 4) / 16;     // 16-carrier work items per symbol (K = 3N/4)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SymSmem &sm = *reinterpret_cast<SymSmem *>(smem_raw);
+    SymSmemOpt &so = *reinterpret_cast<SymSmemOpt *>(smem_raw + sizeof(SymSmem));   // OPT only
 
     const int tid = threadIdx.x;
     const int tf = blockIdx.x / p.n_chunks;
@@ -208,6 +256,8 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
     const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
     const size_t out_base = (size_t)tf * p.tf_samples;
     const bool tii_on = p.tii_count > 0 && (((p.tf_offset + tf + p.tii_parity) & 1) == 0);
+    const int W = OPT ? p.window : 0;
+    const bool cfr = OPT && p.cfr != 0;
 
     // ---- per-CTA tables ----
     for (int i = tid; i < p.n_twiddle; i += SYM_THREADS) sm.tw[i] = __ldg(p.twiddle + i);
@@ -224,6 +274,24 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
         const float c[8] = {1.f, v, 0.f, -v, -1.f, -v, 0.f, v};
         sm.c8[tid] = make_float2(c[tid], c[(tid + 6) & 7]);
     }
+    if (OPT) {
+        for (int i = tid; i < 2 * W; i += SYM_THREADS) {
+            so.win[i] = __ldg(p.window_tab + i);
+            so.tail[0][i] = make_float2(0.f, 0.f);
+            so.tail[1][i] = make_float2(0.f, 0.f);
+        }
+    }
+
+    // ---- iteration schedule over symbol groups ----
+    //   plain:  the chunk's groups in order, except that TM I (G == 1) runs group 1 before
+    //           group 0: the null symbol takes the gain of symbol 1 (GainControl.cpp:139-144)
+    //   window: groups in natural order (each symbol needs the falling edge of its
+    //           predecessor), preceded by one extra iteration: the group before the chunk
+    //           (tail only), or for TM I chunk 0 group 1 (gain only).
+    enum { EMIT = 0, TAIL_ONLY = 1, GAIN_ONLY = 2 };
+    const bool win_pre = W > 0 && (grp0 > 0 || G == 1);
+    const int n_iter = (grp1 - grp0) + (win_pre ? 1 : 0);
+    const int g_first = (W > 0 && grp0 > 0) ? grp0 - 1 : grp0;   // first group whose data bits are consumed
 
     // ---- carrier work item of this thread: 16 consecutive source carriers ----
     // thread (g, jj): symbol g of the group, carriers 16*jj .. 16*jj+15
@@ -239,11 +307,10 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
     }
     __syncthreads();
 
-    // Phase prefix: consume the data symbols that precede this chunk.
+    // Phase prefix: consume the data symbols that precede the first group.
     // Symbol s >= 2 carries data symbol d = s - 2.
     {
-        const int s_first = grp0 * G;
-        const int nd = max(0, s_first - 2);
+        const int nd = max(0, g_first * G - 2);
         if (carrier_thread) {
             const uint8_t *row = bits + 2 * jj;
             for (int d = 0; d < nd; d++, row += K / 4) {
@@ -257,19 +324,24 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
 
     unsigned clip = 0;
     float gain_sym1 = 1.0f;
-    for (int gi = grp0; gi < grp1; gi++) {
-        int grp = gi;
-        if (G == 1 && grp0 == 0) {
-            // TM I: the null symbol (group 0) needs the gain of symbol 1 (group 1):
-            // run group 1 first.  Neither consumes data bits.
-            grp = gi == 0 ? 1 : gi == 1 ? 0 : gi;
-            if (grp == 0 && !tii_on) {
-                // plain null symbol: all-zero carriers -> all-zero samples
-                const size_t pos = out_base;
-                for (int i = tid; i < p.null_size; i += SYM_THREADS)
-                    store_sample<POST>(p.out, pos + i, make_float2(0.f, 0.f), p.post, clip);
-                continue;
-            }
+    int tail_par = 0;
+    for (int it = 0; it < n_iter; it++) {
+        int grp, what = EMIT;
+        if (W > 0) {
+            if (grp0 > 0) { grp = grp0 - 1 + it; what = it == 0 ? TAIL_ONLY : EMIT; }
+            else if (G == 1) { grp = it == 0 ? 1 : it - 1; what = it == 0 ? GAIN_ONLY : EMIT; }
+            else grp = it;
+        }
+        else {
+            grp = grp0 + it;
+            if (G == 1 && grp0 == 0) grp = it == 0 ? 1 : it == 1 ? 0 : it;   // neither consumes data bits
+        }
+        if (!OPT && G == 1 && grp == 0 && !tii_on) {
+            // plain null symbol: all-zero carriers -> all-zero samples
+            const size_t pos = out_base;
+            for (int i = tid; i < p.null_size; i += SYM_THREADS)
+                store_sample<POST>(p.out, pos + i, make_float2(0.f, 0.f), p.post, clip);
+            continue;
         }
         const int s0 = grp * G;   // first symbol of the group
         // ---- 1. frequency-domain symbols into the shared buffer ----
@@ -322,16 +394,59 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
         if (grp == 0 && tii_on) __syncthreads();
 
         // ---- 2. inverse FFT of the G symbols, in place ----
-        // Per-pass twiddle tables (see StockhamPass): pass 2 at sm.tw, pass 3 behind it.
-        // ---- 3. gain: statistics per symbol over its N samples ----
         // thread (eg, tt): symbol eg of the group, samples tt + TG*i
         const int eg = tid / TG, tt = tid - eg * TG;
         float2 x[16];
-        if (N == 2048) {
-            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-            { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw);
-              __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
+        if (OPT) {
+            if (cfr) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int e = spad(tid + SYM_THREADS * i);
+                    so.ref[e] = sm.buf[e];
+                }
+            }
+            sym_fft<N, true>(sm.buf, sm.tw, tid);
+            if (cfr) {
+                // ---- 2'. one CFR iteration (OfdmGenerator.cpp:310-373) ----
+                const float clip_sq = p.cfr_clip * p.cfr_clip;
+                const float err_sq = p.cfr_errclip * p.cfr_errclip;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int e = spad(tid + SYM_THREADS * i);
+                    float2 v = sm.buf[e];
+                    const float mag = v.x * v.x + v.y * v.y;
+                    if (mag > clip_sq) {
+                        const float f = sqrtf(clip_sq / mag);
+                        v.x *= f; v.y *= f;
+                        sm.buf[e] = v;
+                    }
+                }
+                __syncthreads();
+                sym_fft<N, false>(sm.buf, sm.tw, tid);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int e = spad(tid + SYM_THREADS * i);
+                    const float2 f = sm.buf[e];
+                    const float2 pt = make_float2(f.x * (1.0f / N), f.y * (1.0f / N));
+                    const float2 r = so.ref[e];
+                    float2 err = make_float2(r.x - pt.x, r.y - pt.y);
+                    const float mag = err.x * err.x + err.y * err.y;
+                    if (mag > err_sq) {
+                        const float s = sqrtf(err_sq / mag);
+                        err.x *= s; err.y *= s;
+                    }
+                    sm.buf[e] = make_float2(pt.x + err.x, pt.y + err.y);
+                }
+                __syncthreads();
+                sym_fft<N, true>(sm.buf, sm.tw, tid);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) x[i] = sm.buf[spad(eg * N + tt + TG * i)];
+        }
+        else if (N == 2048) {
+            // Per-pass twiddle tables (see StockhamPass): pass 2 at sm.tw, pass 3 behind it.
+            sym_pass<16, true, 1, N>(sm.buf, tid, 1, sm.tw);
+            sym_pass<16, true, 1, N>(sm.buf, tid, 16, sm.tw);
             // last pass stays in registers: butterfly p of this thread yields samples
             // tid + 128*p + 256*r, i.e. x[2r + p] of the emit layout (TG = 128)
             StockhamPass<8, true, 2> ps;
@@ -340,31 +455,11 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
             for (int r = 0; r < 8; r++) { x[2 * r] = ps.v[0][r]; x[2 * r + 1] = ps.v[1][r]; }
         }
         else {
-            if (N == 1024) {
-                { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
-                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 128, sm.tw + 7 * 16);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 128); __syncthreads(); }
-            }
-            else if (N == 512) {
-                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 8, sm.tw);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 8); __syncthreads(); }
-                { StockhamPass<8, true, 2> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 64, sm.tw + 7 * 8);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 64); __syncthreads(); }
-            }
-            else {
-                { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 1, sm.tw);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 1); __syncthreads(); }
-                { StockhamPass<16, true, 1> ps; ps.load(sm.buf, tid, SYM_THREADS, N, 16, sm.tw);
-                  __syncthreads(); ps.store(sm.buf, tid, SYM_THREADS, N, 16); __syncthreads(); }
-            }
+            sym_fft<N, true>(sm.buf, sm.tw, tid);
 #pragma unroll
             for (int i = 0; i < 16; i++) x[i] = sm.buf[spad(eg * N + tt + TG * i)];
         }
+        // ---- 3. gain: statistics per symbol over its N samples ----
         float g_sym;
         if (p.gain_mode == 0) {
             g_sym = 512.0f;
@@ -454,20 +549,75 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
         g_sym *= p.gain_const;
 
         // ---- 4. guard interval + store ----
-        const int s = s0 + eg;
-        if (s <= p.L) {
-            const int size = s == 0 ? p.null_size : p.sym_size;
-            const int pre = size - N;
-            const size_t pos = out_base + sym_pos(p, s);
+        if (W == 0) {
+            const int s = s0 + eg;
+            if (s <= p.L) {
+                const int size = s == 0 ? p.null_size : p.sym_size;
+                const int pre = size - N;
+                const size_t pos = out_base + sym_pos(p, s);
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int n = tt + TG * i;
-                const float2 v = make_float2(x[i].x * g_sym, x[i].y * g_sym);
-                store_sample<POST>(p.out, pos + pre + n, v, p.post, clip);
-                if (n >= N - pre) store_sample<POST>(p.out, pos + n - (N - pre), v, p.post, clip);
+                for (int i = 0; i < 16; i++) {
+                    const int n = tt + TG * i;
+                    const float2 v = make_float2(x[i].x * g_sym, x[i].y * g_sym);
+                    store_sample<POST>(p.out, pos + pre + n, v, p.post, clip);
+                    if (n >= N - pre) store_sample<POST>(p.out, pos + n - (N - pre), v, p.post, clip);
+                }
+            }
+            __syncthreads();
+        }
+        else if (OPT) {
+            // Windowed guard interval.  With pos = start of symbol s in the TF and `size` its
+            // length, the symbol's cyclic extension ext(o) = x[(o - pre) mod N] covers
+            // o in [-W, size + W); it rises with win[o + W] over [-W, W) and falls with
+            // win[2W-1-(o-(size-W))] over [size-W, size+W); overlapping edges of neighbours
+            // add.  The owner of symbol s writes [pos - W, pos + size - W): both
+            // contributions of its leading overlap, none of the trailing one.  The null
+            // symbol has no rising edge, the last symbol no falling edge.
+            // (each thread overwrites exactly the elements it loaded into x[])
+            if (what != GAIN_ONLY) {
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    sm.buf[spad(eg * N + tt + TG * i)] = make_float2(x[i].x * g_sym, x[i].y * g_sym);
+            }
+            __syncthreads();
+            if (what != GAIN_ONLY) {
+                for (int g = 0; g < G; g++) {
+                    const int s = s0 + g;
+                    if (s > p.L) break;
+                    const int size = s == 0 ? p.null_size : p.sym_size;
+                    const int pre = size - N;
+                    const bool first = s == 0, last = s == p.L;
+                    const float2 *cur = so.tail[tail_par];
+                    float2 *nxt = so.tail[tail_par ^ 1];
+                    const float2 *xs = sm.buf;
+                    if (what == EMIT) {
+                        const long long pos = (long long)out_base + sym_pos(p, s);
+                        for (int o = (first ? 0 : -W) + tid; o < (last ? size : size - W); o += SYM_THREADS) {
+                            int idx = o - pre;
+                            if (idx < 0) idx += N;
+                            float2 v = xs[spad(g * N + idx)];
+                            if (!first && o < W) {
+                                const float w = so.win[o + W];
+                                const float2 t = cur[o + W];
+                                v = make_float2(fmaf(v.x, w, t.x), fmaf(v.y, w, t.y));
+                            }
+                            store_sample<POST>(p.out, (size_t)(pos + o), v, p.post, clip);
+                        }
+                    }
+                    if (!last) {
+                        for (int i = tid; i < 2 * W; i += SYM_THREADS) {
+                            int idx = N - W + i;          // ext(size - W + i)
+                            if (idx >= N) idx -= N;
+                            const float2 v = xs[spad(g * N + idx)];
+                            const float w = so.win[2 * W - 1 - i];
+                            nxt[i] = make_float2(v.x * w, v.y * w);
+                        }
+                    }
+                    tail_par ^= 1;
+                    __syncthreads();
+                }
             }
         }
-        __syncthreads();
     }
     if (POST && p.post.format != 0) flush_clip(p.post, clip);
 }

@@ -248,3 +248,85 @@ def test_full_chain_c3_c5(dm, rng):
         out = dm.Modulator(max_batch=2, **kw).process_batch(bits)
         for i in range(2):
             assert rel_rms(out[i], ora[i]) < TOL
+
+
+# ---------------------------------------------------------------------------
+# Optional features of the same blocks: OFDM windowing, crest factor reduction
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,W", [(1, 10), (1, 504), (2, 7), (3, 4), (3, 63), (4, 32), (4, 252)])
+def test_ofdm_windowing(dm, rng, mode, W):
+    """GuardIntervalInserter.cpp:149-300; W up to the full guard interval, every chunking."""
+    bits = bits_for(rng, mode, 2)
+    ora = oracle.OracleChain(mode=mode, window_overlap=W).run(bits)
+    mod = dm.Modulator(mode=mode, window_overlap=W, max_batch=2)
+    assert mod.get_param("windowlen") == str(W)
+    ref = None
+    for chunks in (0, 1, 2, 5):
+        mod.set_param("sym_chunks", chunks)
+        out = mod.process_batch(bits)
+        for i in range(2):
+            assert rel_rms(out[i], ora[i]) < TOL, (chunks, i)
+        if ref is None:
+            ref = out.copy()
+        else:   # the chunking never changes a bit
+            assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), chunks
+
+
+def test_ofdm_windowing_rc_and_chain(dm, rng):
+    """windowlen through the remote-control surface, with TII, FIR and s16 behind it."""
+    bits = bits_for(rng, 2, 3)
+    taps = oracle.fir_default_taps()
+    kw = dict(mode=2, tii=(4, 17, 0), fir_taps=taps, digital_gain=0.8, fmt="s16")
+    mod = dm.Modulator(max_batch=3, **kw)
+    mod.set_param("windowlen", 20)
+    out = mod.process_batch(bits)
+    ora = oracle.OracleChain(window_overlap=20, **kw).run(bits)
+    for i in range(3):
+        d = np.abs(out[i].astype(np.int32) - ora[i].astype(np.int32))
+        assert d.max() <= 1 and np.count_nonzero(d) < 1e-3 * d.size, i
+    with pytest.raises(dm.DabModError):
+        mod.set_param("windowlen", 127)      # TM II guard interval is 126 samples
+    mod.set_param("windowlen", 0)
+    mod.reset()
+    plain = mod.process_batch(bits)
+    ora0 = oracle.OracleChain(**kw).run(bits)
+    for i in range(3):
+        d = np.abs(plain[i].astype(np.int32) - ora0[i].astype(np.int32))
+        assert d.max() <= 1, i
+
+
+@pytest.mark.parametrize("mode,clip,errclip", [(1, 50.0, 0.1), (1, 70.0, 0.02), (2, 25.0, 0.1), (3, 18.0, 0.05),
+                                               (4, 35.0, 0.2)])
+def test_cfr(dm, rng, mode, clip, errclip):
+    """OfdmGeneratorCF32::cfr_one_iteration (OfdmGenerator.cpp:310-373)."""
+    bits = bits_for(rng, mode, 2)
+    ora = oracle.OracleChain(mode=mode, cfr=(clip, errclip)).run(bits)
+    plain = oracle.OracleChain(mode=mode).run(bits)
+    assert rel_rms(plain[0], ora[0]) > 1e-3          # the parameters do clip
+    mod = dm.Modulator(mode=mode, cfr=(clip, errclip), max_batch=2)
+    out = mod.process_batch(bits)
+    for i in range(2):
+        assert rel_rms(out[i], ora[i]) < TOL, i
+    # remote control: switch it off, change the thresholds, switch it on again
+    mod.set_param("cfr", 0)
+    off = mod.process_batch(bits)
+    assert rel_rms(off[0], plain[0]) < TOL
+    mod.set_param("clip", clip * 0.8)
+    mod.set_param("errorclip", errclip * 2)
+    mod.set_param("cfr", 1)
+    out2 = mod.process_batch(bits)
+    ora2 = oracle.OracleChain(mode=mode, cfr=(clip * 0.8, errclip * 2)).run(bits)
+    for i in range(2):
+        assert rel_rms(out2[i], ora2[i]) < TOL, i
+
+
+def test_cfr_with_window_tii_fir_resampler(dm, rng):
+    """Everything optional at once on TM I."""
+    bits = bits_for(rng, 1, 2)
+    taps = oracle.fir_default_taps()
+    kw = dict(mode=1, cfr=(50.0, 0.1), window_overlap=16, tii=(1, 11, 0), fir_taps=taps,
+              output_rate=4096000, gain_mode="max")
+    ora = oracle.OracleChain(**kw).run(bits)
+    out = dm.Modulator(max_batch=2, **kw).process_batch(bits)
+    for i in range(2):
+        assert rel_rms(out[i], ora[i]) < TOL, i
