@@ -296,7 +296,8 @@ def gpu_arm(args):
     e2e_value = eti_per_step * e2e_steps / e2e_s
 
     peak, peak_src = measured_peaks()
-    bytes_per_launch = {"k_symbols": SYM_BYTES_PER_TF * n_tf, "k_fir": FIR_BYTES_PER_TF * n_tf}
+    bytes_per_launch = {"k_symbols": SYM_BYTES_PER_TF * n_tf, "k_symbols_w": SYM_BYTES_PER_TF * n_tf,
+                        "k_fir": FIR_BYTES_PER_TF * n_tf}
     dom = max(kavg, key=lambda k: kavg[k])
     achieved = bytes_per_launch[dom] / (kavg[dom] * 1e-3) / 1e9
     roofline = {

@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "resample.cuh"
+#include "symbols_warp.cuh"
 #include "tables.h"
 
 using namespace dabmod;
@@ -102,6 +103,8 @@ struct dabmod_b200 {
     DevBuf<uint8_t> d_phase0;
     DevBuf<float> d_cic;
     DevBuf<float> d_twiddle;       // interleaved re/im, per-pass tables (symbol_fft_twiddles)
+    DevBuf<float> d_twiddle_w;     // second-pass table of k_symbols_w (TM I only)
+    bool use_warp_kernel = true;   // "sym_kernel" knob: 0 = always the CTA-per-symbol-group kernel
     int n_twiddle = 0;
     DevBuf<uint16_t> d_tii_bin;
     DevBuf<float> d_tii_val;
@@ -349,6 +352,38 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     sp.post = make_post(h, sym_post);
 
     const bool sym_opt = c.cfr_enable != 0 || c.window_overlap > 0;
+    // TM I without the optional per-carrier features: one warp per symbol (symbols_warp.cuh)
+    if (m.N == SW_N && h->use_warp_kernel && !sym_opt && !h->use_cic && h->tii_count == 0) {
+        SymWParams wp{};
+        wp.s = sp;
+        wp.twiddle_w = reinterpret_cast<const float2 *>(h->d_twiddle_w.p);
+        wp.n_tf = (int)n_tf;
+        // enough (TF, chunk) items for ~8 per resident warp; chunks short enough to balance,
+        // long enough to amortise the phase prefix
+        const size_t slots = (size_t)h->sm_count * SW_WARPS;
+        int chunks = (int)std::min<size_t>((size_t)sp.n_groups, std::max<size_t>(1, (8 * slots + n_tf - 1) / n_tf));
+        chunks = std::min(chunks, 39);
+        if (h->force_chunks > 0) chunks = std::min(h->force_chunks, sp.n_groups);
+        wp.s.groups_per_chunk = (sp.n_groups + chunks - 1) / chunks;
+        wp.s.n_chunks = (sp.n_groups + wp.s.groups_per_chunk - 1) / wp.s.groups_per_chunk;
+        const long long items = (long long)n_tf * wp.s.n_chunks;
+        const int wgrid = (int)std::min<long long>((items + SW_WARPS - 1) / SW_WARPS, h->sm_count);
+        ProfScope prof_w(h, "k_symbols_w", s);
+        if (sym_post) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_symbols_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(SymWSmem)));
+            k_symbols_w<true><<<wgrid, SW_THREADS, sizeof(SymWSmem), s>>>(wp);
+        }
+        else {
+            CUDA_CHECK(cudaFuncSetAttribute(k_symbols_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(SymWSmem)));
+            k_symbols_w<false><<<wgrid, SW_THREADS, sizeof(SymWSmem), s>>>(wp);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        prof_w.end();
+        launches++;
+    }
+    else {
     const int grid = (int)(n_tf * sp.n_chunks);
     ProfScope prof_sym(h, "k_symbols", s);
     switch (m.N) {
@@ -360,6 +395,7 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     CUDA_CHECK(cudaGetLastError());
     prof_sym.end();
     launches++;
+    }
 
     if (fir) {
         FirParams fp{};
@@ -557,6 +593,17 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
         symbol_fft_twiddles(h->m.N, tw);
         h->d_twiddle.upload(tw, h->s_compute);
         h->n_twiddle = (int)(tw.size() / 2);
+        if (h->m.N == SW_N) {
+            std::vector<float> tww;
+            for (int r = 1; r < 32; r++)
+                for (int j = 0; j < 64; j++) {
+                    const double a = 2.0 * M_PI * (double)j * (double)r / (double)SW_N;
+                    tww.push_back((float)cos(a));
+                    tww.push_back((float)sin(a));
+                }
+            h->d_twiddle_w.upload(tww, h->s_compute);
+            CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+        }
         h->d_clipped.alloc(1);
         CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
         build_tables(h);
@@ -637,6 +684,8 @@ int dabmod_b200_process_batch_device(dabmod_b200 *h, const uint8_t *d_bits, size
         if (!h || (n_tf && (!d_bits || !d_iq_out))) throw ApiError(DABMOD_B200_EINVAL, "null argument");
         if (n_tf > (size_t)h->cfg.max_batch)
             throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
+        if ((reinterpret_cast<uintptr_t>(d_bits) & 3) || (reinterpret_cast<uintptr_t>(d_iq_out) & 15))
+            throw ApiError(DABMOD_B200_EINVAL, "device buffers must be aligned (bits: 4 bytes, I/Q: 16 bytes)");
         std::lock_guard<std::mutex> lock(h->mtx);
         CUDA_CHECK(cudaSetDevice(h->device));
         cudaStream_t s = stream ? (cudaStream_t)stream : h->s_compute;
@@ -792,6 +841,7 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             if (n == "digital") { ss >> c.digital_gain; }
             else if (n == "profile") { int v; ss >> v; h->profile = v != 0; }
             else if (n == "sym_chunks") { int v; ss >> v; h->force_chunks = v < 0 ? 0 : v; }
+            else if (n == "sym_kernel") { int v; ss >> v; h->use_warp_kernel = v != 0; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {
                 std::string v; ss >> v;

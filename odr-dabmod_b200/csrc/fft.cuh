@@ -7,29 +7,35 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// The pure butterfly arithmetic can also be compiled for the host (tests/test_fft_host.py
+// checks it on the CPU); kernels see plain __device__ functions.
+#ifndef DABMOD_FN
+#define DABMOD_FN __device__ __forceinline__
+#endif
+
 namespace dabmod {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+DABMOD_FN float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DABMOD_FN float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+DABMOD_FN float2 cmul(float2 a, float2 b)
 {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 // multiply by +j (INV) or -j (forward)
 template <bool INV>
-__device__ __forceinline__ float2 mul_j(float2 a)
+DABMOD_FN float2 mul_j(float2 a)
 {
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
 // twiddle table holds e^{+j theta}; the forward transform needs the conjugate
 template <bool INV>
-__device__ __forceinline__ float2 tw_dir(float2 w)
+DABMOD_FN float2 tw_dir(float2 w)
 {
     return INV ? w : make_float2(w.x, -w.y);
 }
 
 template <bool INV>
-__device__ __forceinline__ void fft2(float2 &a, float2 &b)
+DABMOD_FN void fft2(float2 &a, float2 &b)
 {
     const float2 t = a;
     a = cadd(t, b);
@@ -37,7 +43,7 @@ __device__ __forceinline__ void fft2(float2 &a, float2 &b)
 }
 
 template <bool INV>
-__device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+DABMOD_FN void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
 {
     const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
     const float2 t2 = cadd(a1, a3), t3 = mul_j<INV>(csub(a1, a3));
@@ -49,7 +55,7 @@ __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 
 
 // v[0..7] natural order in, natural order out
 template <bool INV>
-__device__ __forceinline__ void fft8(float2 *v)
+DABMOD_FN void fft8(float2 *v)
 {
     const float h = 0.70710678118654752440f;
     float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
@@ -70,7 +76,7 @@ __device__ __forceinline__ void fft8(float2 *v)
 
 // v[0..15] natural order in, natural order out (4 x 4 decomposition)
 template <bool INV>
-__device__ __forceinline__ void fft16(float2 *v)
+DABMOD_FN void fft16(float2 *v)
 {
     // cos/sin of 2 pi e / 16
     const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
@@ -107,7 +113,7 @@ __device__ __forceinline__ void fft16(float2 *v)
 }
 
 template <int R, bool INV>
-__device__ __forceinline__ void fft_radix(float2 *v)
+DABMOD_FN void fft_radix(float2 *v)
 {
     static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
     if (R == 2) fft2<INV>(v[0], v[1]);

@@ -1,0 +1,303 @@
+// k_symbols_w: the TM I (N = 2048) symbol kernel, one WARP per OFDM symbol.
+//
+// Same chain as k_symbols (kernels.cuh) for the plain configuration -- no CicEq,
+// no CFR, no windowing, no TII frame -- i.e. reference QpskSymbolMapper.cpp:105-156,
+// FrequencyInterleaver.cpp:103-126, DifferentialModulator.cpp:45-76,
+// SignalMultiplexer.cpp:45-71 (NullSymbol), OfdmGenerator.cpp:157-308,
+// GainControl.cpp:82-340, GuardIntervalInserter.cpp:301-319.
+//
+// Why a second kernel: k_symbols is bound by the shared-memory/LSU data pipe
+// (128 B/clk/SM): a 2048-point transform done as 16 x 16 x 8 by 128 threads crosses
+// shared memory twice and synchronises the CTA six times per symbol.  Here a warp
+// owns the whole symbol: every lane holds 64 points in registers, the transform is
+// 64 x 32 (fft_reg.cuh), so the data crosses shared memory ONCE, and the only
+// synchronisation is __syncwarp.  Per symbol the LSU moves ~0.9 k wavefronts
+// instead of ~1.9 k, which is what the HBM write stream (910 clk/symbol/SM) needs.
+//
+// Work item of a warp = (TF, chunk of consecutive symbols), as in k_symbols; the
+// differential phases at the chunk start are obtained by bit-sliced counting over
+// the preceding bit rows (2-bit counter of i^q and parity of q per carrier).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fft_reg.cuh"
+#include "kernels.cuh"
+
+namespace dabmod {
+
+constexpr int SW_WARPS = 12;                // warps (= symbols in flight) per CTA
+constexpr int SW_THREADS = SW_WARPS * 32;
+constexpr int SW_XPAD = 65;                 // lane stride (complex) of the exchange buffer
+constexpr int SW_N = 2048, SW_K = 1536;
+constexpr int SW_CPL = SW_K / 32;           // 48 source carriers per lane
+
+struct SymWSmem {
+    float2 tw[31 * 64];                     // second pass twiddles: tw[(r-1)*64 + j] = e^{+j 2 pi j r / 2048}
+    uint32_t bin_t[SW_CPL / 2 * 32];        // bin_of_src transposed, two per word: [i/2][lane] holds the FFT bins of
+                                            // source carriers 48*lane + i, i even (low half) and i + 1 (high half)
+    uint32_t spread[256];
+    float2 c8[16];                          // value of phase code 0..7 (units of pi/4); code 8 = empty bin
+    float2 x[SW_WARPS][32 * SW_XPAD];       // per-warp exchange buffer; its first 2048 bytes double as the
+                                            // per-bin phase-code staging of the next symbol
+};
+
+struct SymWParams {
+    SymParams s;                            // shared with k_symbols
+    const float2 *twiddle_w;                // 31 * 64 entries
+    int n_tf;
+};
+
+// I/Q bit bytes of the lane's 48 carriers in one bit row: 6 bytes each, as (4 bytes, 2 bytes)
+struct RowBits { uint32_t i_lo, i_hi, q_lo, q_hi; };
+
+// The lane's 6 bytes start at byte 6*lane (2-byte aligned): two aligned 32-bit loads cover them.
+__device__ __forceinline__ void sw_load6(const uint8_t *p6, uint32_t &lo, uint32_t &hi)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p6);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
+    const unsigned sh = (unsigned)(a & 2) * 8;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = (w1 >> sh) & 0xffffu;
+}
+
+__device__ __forceinline__ RowBits sw_load_row(const uint8_t *row, int lane)
+{
+    RowBits b;
+    sw_load6(row + 6 * lane, b.i_lo, b.i_hi);
+    sw_load6(row + SW_K / 8 + 6 * lane, b.q_lo, b.q_hi);
+    return b;
+}
+
+template <bool POST>
+__global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_constant__ SymWParams pw)
+{
+    const SymParams &p = pw.s;
+    constexpr int N = SW_N, K = SW_K;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SymWSmem &sm = *reinterpret_cast<SymWSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- per-CTA tables ----
+    for (int i = tid; i < 31 * 64; i += SW_THREADS) sm.tw[i] = __ldg(pw.twiddle_w + i);
+    for (int i = tid; i < K / 2; i += SW_THREADS) {
+        const int l = i / (SW_CPL / 2), c = i - l * (SW_CPL / 2);
+        sm.bin_t[c * 32 + l] = __ldg(reinterpret_cast<const uint32_t *>(p.bin_of_src) + i);
+    }
+    for (int b = tid; b < 256; b += SW_THREADS) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int n = 0; n < 8; n++) s |= ((b >> (7 - n)) & 1u) << (4 * n);
+        sm.spread[b] = s;
+    }
+    if (tid < 16) {
+        // exactly the values the reference's float32 product chain takes:
+        // {1, v, 0, -v, -1} with v = (float)M_SQRT1_2 (v*v rounds to 0.5)
+        const float v = 0.70710678118654752440f;
+        const float c[8] = {1.f, v, 0.f, -v, -1.f, -v, 0.f, v};
+        sm.c8[tid] = tid < 8 ? make_float2(c[tid], c[(tid + 6) & 7]) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+
+    // Persistent CTA (one per SM): round r = the SW_WARPS work items r*SW_WARPS .. +SW_WARPS-1
+    unsigned clip = 0;
+    const long long n_items = (long long)pw.n_tf * p.n_chunks;
+    const long long n_rounds = (n_items + SW_WARPS - 1) / SW_WARPS;
+    for (long long round = blockIdx.x; round < n_rounds; round += gridDim.x) {
+        // a warp beyond the last item idles through the barriers of the round
+        const long long item_raw = round * SW_WARPS + warp;
+        const bool valid = item_raw < n_items;
+        const long long item = valid ? item_raw : 0;
+        const int tf = (int)(item / p.n_chunks);
+        const int chunk = (int)(item - (long long)tf * p.n_chunks);
+        const int sym0 = chunk * p.groups_per_chunk;
+        const int sym1 = min(sym0 + p.groups_per_chunk, p.n_groups);
+        const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
+        const size_t out_base = (size_t)tf * p.tf_samples;
+        float2 *xb = sm.x[warp];
+        uint8_t *code = reinterpret_cast<uint8_t *>(xb);
+
+        // ---- running phase of the lane's 48 source carriers, 8 nibbles per word ----
+        uint32_t ph[6];
+    #pragma unroll
+        for (int w = 0; w < 6; w++) {
+            uint32_t v = 0;
+    #pragma unroll
+            for (int n = 0; n < 8; n++) v |= (uint32_t)__ldg(p.phase0 + SW_CPL * lane + 8 * w + n) << (4 * n);
+            ph[w] = v;
+        }
+        // Phase prefix: symbol s >= 2 carries data row d = s - 2.  Rows before the chunk are
+        // summed bit-sliced: increment = 1 + 2 (i ^ q) + 4 q (units of pi/4), so
+        // sum = nd + 2 (c0 + 2 c1) + 4 pq with (c1 c0) a 2-bit counter of i^q, pq the parity of q.
+        {
+            const int nd = max(0, sym0 - 2);
+            uint32_t c0l = 0, c0h = 0, c1l = 0, c1h = 0, pql = 0, pqh = 0;
+            const uint8_t *row = bits;
+    #pragma unroll 16
+            for (int d = 0; d < nd; d++, row += K / 4) {
+                const RowBits b = sw_load_row(row, lane);
+                const uint32_t xl = b.i_lo ^ b.q_lo, xh = b.i_hi ^ b.q_hi;
+                c1l ^= c0l & xl; c1h ^= c0h & xh;
+                c0l ^= xl; c0h ^= xh;
+                pql ^= b.q_lo; pqh ^= b.q_hi;
+            }
+            const uint32_t base = (uint32_t)(nd & 7) * 0x11111111u;
+            const uint32_t m2l = c1l ^ pql, m2h = c1h ^ pqh;
+    #pragma unroll
+            for (int w = 0; w < 6; w++) {
+                const uint32_t b0 = ((w < 4 ? c0l >> (8 * w) : c0h >> (8 * (w - 4)))) & 0xffu;
+                const uint32_t b1 = ((w < 4 ? m2l >> (8 * w) : m2h >> (8 * (w - 4)))) & 0xffu;
+                const uint32_t t = (base + 2u * sm.spread[b0] + 4u * sm.spread[b1]) & 0x77777777u;
+                ph[w] = (ph[w] + t) & 0x77777777u;
+            }
+        }
+
+        // bit row of the first data symbol of the chunk, then always one symbol ahead
+        RowBits nextrow = {0, 0, 0, 0};
+        {
+            const int s_first_data = max(sym0, 2);
+            if (s_first_data < sym1) nextrow = sw_load_row(bits + (size_t)(s_first_data - 2) * (K / 4), lane);
+        }
+        // The warps of a CTA walk through their chunks in step (one barrier per symbol): the
+        // loop body is ~60 KB of straight-line code, far beyond the instruction cache, and
+        // warps at different places in it would each stream it separately.
+        for (int it = 0; it < p.groups_per_chunk; it++) {
+            __syncthreads();
+            const int s = sym0 + it;
+            if (!valid || s >= sym1) continue;
+            if (s == 0) {
+                // null symbol without TII: all-zero carriers -> all-zero samples, whatever gain
+                // it borrows from symbol 1 (GainControl.cpp:139-144)
+                for (int i = lane; i < p.null_size; i += 32)
+                    store_sample<POST>(p.out, out_base + i, make_float2(0.f, 0.f), p.post, clip);
+                continue;
+            }
+            // ---- 1. differential phase of this symbol, scattered by FFT bin as byte codes ----
+            if (s >= 2) {
+                const RowBits b = nextrow;
+                if (s + 1 < sym1) nextrow = sw_load_row(bits + (size_t)(s - 1) * (K / 4), lane);
+    #pragma unroll
+                for (int w = 0; w < 6; w++) {
+                    const uint32_t ib = ((w < 4 ? b.i_lo >> (8 * w) : b.i_hi >> (8 * (w - 4)))) & 0xffu;
+                    const uint32_t qb = ((w < 4 ? b.q_lo >> (8 * w) : b.q_hi >> (8 * (w - 4)))) & 0xffu;
+                    ph[w] = (ph[w] + phase_step(sm.spread, ib, qb)) & 0x77777777u;
+                }
+            }
+                // (all table loads first: the compiler cannot tell that the byte stores below
+            // never hit the table, and would otherwise order every load behind a store)
+            uint32_t bins[SW_CPL / 2];
+#pragma unroll
+            for (int i = 0; i < SW_CPL / 2; i++) bins[i] = sm.bin_t[i * 32 + lane];
+#pragma unroll
+            for (int i = 0; i < SW_CPL; i++) {
+                const uint32_t c = (ph[i >> 3] >> (4 * (i & 7))) & 7u;
+                const uint32_t bin = (i & 1) ? bins[i >> 1] >> 16 : bins[i >> 1] & 0xffffu;
+                code[bin] = (uint8_t)c;
+            }
+            __syncwarp();
+
+            // ---- 2. inverse FFT, pass 1: lane owns bins lane + 32 r, r < 64 (radix 64) ----
+            // Bins 769..1279 and bin 0 are empty (OfdmGenerator.cpp:207-220): r in 25..39 for
+            // every lane, r = 24 except lane 0, r = 0 for lane 0.
+            float2 v[64];
+    #pragma unroll
+            for (int r = 0; r < 64; r++) {
+                if (r >= 25 && r <= 39) {
+                    v[r] = make_float2(0.f, 0.f);
+                }
+                else {
+                    uint32_t c = code[lane + 32 * r];
+                    if (r == 0 && lane == 0) c = 8;
+                    if (r == 24 && lane != 0) c = 8;
+                    v[r] = sm.c8[c];
+                }
+            }
+            fft64<true>(v);
+            __syncwarp();                        // all codes read before the buffer is overwritten
+    #pragma unroll
+            for (int r = 0; r < 64; r++) xb[lane * SW_XPAD + r] = v[r];
+            __syncwarp();
+            // ---- pass 2: butterflies j = lane and lane + 32 (radix 32), sample n = j + 64 r ----
+            // y[i] = sample lane + 32 i
+            float2 y[64];
+    #pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int j = lane + 32 * h;
+                float2 u[32];
+    #pragma unroll
+                for (int r = 0; r < 32; r++) u[r] = xb[r * SW_XPAD + j];
+    #pragma unroll
+                for (int r = 1; r < 32; r++) u[r] = cmul(u[r], sm.tw[(r - 1) * 64 + j]);
+                fft32<true>(u);
+    #pragma unroll
+                for (int r = 0; r < 32; r++) y[2 * r + h] = u[r];
+            }
+            __syncwarp();                        // buffer free for the next symbol's codes
+
+            // ---- 3. gain (GainControl.cpp:196-340), statistics over the N samples ----
+            float g_sym;
+            if (p.gain_mode == 0) {
+                g_sym = 512.0f;
+            }
+            else if (p.gain_mode == 1) {
+                float mn = y[0].x, mx = y[0].x;
+    #pragma unroll
+                for (int i = 0; i < 64; i++) {
+                    mn = fminf(mn, fminf(y[i].x, y[i].y));
+                    mx = fmaxf(mx, fmaxf(y[i].x, y[i].y));
+                }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                const float m = fmaxf(-mn, mx);
+                g_sym = ((int)m != 0) ? 32767.0f / m : 1.0f;
+            }
+            else {
+                // two-pass mean / variance of re and im separately
+                float sr = 0.f, si = 0.f;
+    #pragma unroll
+                for (int i = 0; i < 64; i++) { sr += y[i].x; si += y[i].y; }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                    si += __shfl_xor_sync(0xffffffffu, si, o);
+                }
+                const float mr = sr * (1.0f / N), mi = si * (1.0f / N);
+                float vr = 0.f, vi = 0.f;
+    #pragma unroll
+                for (int i = 0; i < 64; i++) {
+                    const float dr = y[i].x - mr, di = y[i].y - mi;
+                    vr = fmaf(dr, dr, vr); vi = fmaf(di, di, vi);
+                }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    vr += __shfl_xor_sync(0xffffffffu, vr, o);
+                    vi += __shfl_xor_sync(0xffffffffu, vi, o);
+                }
+                const float sdr = p.var_factor * sqrtf(vr * (1.0f / N));
+                const float sdi = p.var_factor * sqrtf(vi * (1.0f / N));
+                // NULL detection looks at the real part only (GainControl.cpp:331)
+                g_sym = ((int)sdr != 0) ? 32767.0f / fmaxf(sdr, sdi) : 1.0f;
+            }
+            g_sym *= p.gain_const;
+
+            // ---- 4. guard interval + store (GuardIntervalInserter.cpp:301-319) ----
+            {
+                const int pre = p.sym_size - N;
+                const size_t pos = out_base + sym_pos(p, s);
+    #pragma unroll
+                for (int i = 0; i < 64; i++) {
+                    const int n = lane + 32 * i;
+                    const float2 o = make_float2(y[i].x * g_sym, y[i].y * g_sym);
+                    store_sample<POST>(p.out, pos + pre + n, o, p.post, clip);
+                    if (n >= N - pre) store_sample<POST>(p.out, pos + n - (N - pre), o, p.post, clip);
+                }
+            }
+        }
+    }
+    if (POST && p.post.format != 0) flush_clip(p.post, clip);
+}
+
+} // namespace dabmod

@@ -330,3 +330,41 @@ def test_cfr_with_window_tii_fir_resampler(dm, rng):
     out = dm.Modulator(max_batch=2, **kw).process_batch(bits)
     for i in range(2):
         assert rel_rms(out[i], ora[i]) < TOL, i
+
+
+# ---------------------------------------------------------------------------
+# TM I has two symbol kernels: warp-per-symbol (default for the plain chain) and
+# CTA-per-symbol-group (everything else).  Both must meet the oracle under every chunking.
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("gain_mode", ["var", "max", "fix"])
+def test_tm1_symbol_kernels_and_chunking(dm, rng, gain_mode):
+    bits = bits_for(rng, 1, 3)
+    ora = oracle.OracleChain(mode=1, gain_mode=gain_mode).run(bits)
+    mod = dm.Modulator(mode=1, gain_mode=gain_mode, max_batch=3)
+    for kernel in (1, 0):
+        mod.set_param("sym_kernel", kernel)
+        ref = None
+        for chunks in (0, 1, 2, 7, 77):
+            mod.set_param("sym_chunks", chunks)
+            out = mod.process_batch(bits)
+            for i in range(3):
+                assert rel_rms(out[i], ora[i]) < TOL, (kernel, chunks, i)
+            if ref is None:
+                ref = out.copy()
+            else:
+                assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), (kernel, chunks)
+
+
+def test_tm1_warp_kernel_edge_patterns(dm):
+    """All-zero / all-one / alternating bit rows through the warp kernel (phase counters wrap)."""
+    m = oracle.mode_params(1)
+    pats = np.stack([np.zeros(m.tf_bytes, np.uint8), np.full(m.tf_bytes, 0xff, np.uint8),
+                     np.tile(np.array([0xaa, 0x55], np.uint8), m.tf_bytes // 2),
+                     np.arange(m.tf_bytes, dtype=np.uint32).astype(np.uint8)])
+    ora = oracle.OracleChain(mode=1).run(pats)
+    mod = dm.Modulator(mode=1, max_batch=4)
+    for chunks in (0, 3):
+        mod.set_param("sym_chunks", chunks)
+        out = mod.process_batch(pats)
+        for i in range(4):
+            assert rel_rms(out[i], ora[i]) < TOL, (chunks, i)

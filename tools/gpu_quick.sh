@@ -1,6 +1,12 @@
 #!/bin/bash
-# quick visit: microbenchmarks + bench line
-set -x
+# quick: gpu tests + bench line (no profiler)
+TAG=${1:-cur}
 mkdir -p gpurun_out
-./tools/ubench/fp32_pipes > gpurun_out/fp32_pipes.txt 2>&1; cat gpurun_out/fp32_pipes.txt
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_$TAG.json 2> gpurun_out/bench.err; python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_$TAG.json"))
+print("value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"])
+for k,v in d["roofline"]["all_kernels"].items(): print(k, v)
+PY
+tail -5 gpurun_out/bench.err
