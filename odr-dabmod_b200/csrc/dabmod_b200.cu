@@ -358,16 +358,9 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         wp.s = sp;
         wp.twiddle_w = reinterpret_cast<const float2 *>(h->d_twiddle_w.p);
         wp.n_tf = (int)n_tf;
-        // enough (TF, chunk) items for ~8 per resident warp; chunks short enough to balance,
-        // long enough to amortise the phase prefix
-        const size_t slots = (size_t)h->sm_count * SW_WARPS;
-        int chunks = (int)std::min<size_t>((size_t)sp.n_groups, std::max<size_t>(1, (8 * slots + n_tf - 1) / n_tf));
-        chunks = std::min(chunks, 39);
-        if (h->force_chunks > 0) chunks = std::min(h->force_chunks, sp.n_groups);
-        wp.s.groups_per_chunk = (sp.n_groups + chunks - 1) / chunks;
-        wp.s.n_chunks = (sp.n_groups + wp.s.groups_per_chunk - 1) / wp.s.groups_per_chunk;
-        const long long items = (long long)n_tf * wp.s.n_chunks;
-        const int wgrid = (int)std::min<long long>((items + SW_WARPS - 1) / SW_WARPS, h->sm_count);
+        // persistent: one CTA per SM, every warp takes one contiguous range of the batch's symbols
+        const long long n_sym = (long long)n_tf * m.L;
+        const int wgrid = (int)std::min<long long>((n_sym + SW_WARPS - 1) / SW_WARPS, h->sm_count);
         ProfScope prof_w(h, "k_symbols_w", s);
         if (sym_post) {
             CUDA_CHECK(cudaFuncSetAttribute(k_symbols_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

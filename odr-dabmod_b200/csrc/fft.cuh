@@ -15,8 +15,20 @@
 
 namespace dabmod {
 
+// Packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2): one instruction per complex add,
+// same rounding as two scalar operations.  The butterflies are bound by instruction
+// issue, not by the FP32 pipe, so halving the adds is what counts.  Anything that
+// swaps re and im (multiplication by +-j) stays scalar: a packed operand is an aligned
+// register pair and a swap would cost real moves.
+#if defined(__CUDA_ARCH__)
+DABMOD_FN float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+DABMOD_FN float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+DABMOD_FN float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+#else
 DABMOD_FN float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 DABMOD_FN float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+DABMOD_FN float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+#endif
 DABMOD_FN float2 cmul(float2 a, float2 b)
 {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -26,6 +38,17 @@ template <bool INV>
 DABMOD_FN float2 mul_j(float2 a)
 {
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// a + (+-j) b and a - (+-j) b, component-wise (no swapped operand is materialised)
+template <bool INV>
+DABMOD_FN float2 cadd_j(float2 a, float2 b)
+{
+    return INV ? make_float2(a.x - b.y, a.y + b.x) : make_float2(a.x + b.y, a.y - b.x);
+}
+template <bool INV>
+DABMOD_FN float2 csub_j(float2 a, float2 b)
+{
+    return INV ? make_float2(a.x + b.y, a.y - b.x) : make_float2(a.x - b.y, a.y + b.x);
 }
 // twiddle table holds e^{+j theta}; the forward transform needs the conjugate
 template <bool INV>
@@ -46,31 +69,40 @@ template <bool INV>
 DABMOD_FN void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
 {
     const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2);
-    const float2 t2 = cadd(a1, a3), t3 = mul_j<INV>(csub(a1, a3));
+    const float2 t2 = cadd(a1, a3), d = csub(a1, a3);
     a0 = cadd(t0, t2);
-    a1 = cadd(t1, t3);
+    a1 = cadd_j<INV>(t1, d);
     a2 = csub(t0, t2);
-    a3 = csub(t1, t3);
+    a3 = csub_j<INV>(t1, d);
+}
+
+// a * e^{+-j pi O / 4}, O odd
+template <int O, bool INV>
+DABMOD_FN float2 mul_w8(float2 a)
+{
+    const float h = 0.70710678118654752440f;
+    // (1 + j) a = (a.x - a.y, a.x + a.y);  (1 - j) a = (a.x + a.y, a.y - a.x)
+    const float2 p = make_float2(a.x - a.y, a.x + a.y), m = make_float2(a.x + a.y, a.y - a.x);
+    if (O == 1) return cscale(INV ? p : m, h);
+    if (O == 3) return cscale(INV ? make_float2(-m.x, -m.y) : make_float2(-p.x, -p.y), h);
+    if (O == 5) return cscale(INV ? make_float2(-p.x, -p.y) : make_float2(-m.x, -m.y), h);
+    return cscale(INV ? m : p, h);
 }
 
 // v[0..7] natural order in, natural order out
 template <bool INV>
 DABMOD_FN void fft8(float2 *v)
 {
-    const float h = 0.70710678118654752440f;
     float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
     float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
     fft4<INV>(e0, e1, e2, e3);
     fft4<INV>(o0, o1, o2, o3);
     // W8^1 = (1 + sj)/sqrt2, W8^2 = sj, W8^3 = (-1 + sj)/sqrt2, s = +1 (INV) / -1
-    const float2 j1 = mul_j<INV>(o1);
-    o1 = make_float2((o1.x + j1.x) * h, (o1.y + j1.y) * h);
-    o2 = mul_j<INV>(o2);
-    const float2 j3 = mul_j<INV>(o3);
-    o3 = make_float2((j3.x - o3.x) * h, (j3.y - o3.y) * h);
+    o1 = mul_w8<1, INV>(o1);
+    o3 = mul_w8<3, INV>(o3);
     v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
     v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
-    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[2] = cadd_j<INV>(e2, o2); v[6] = csub_j<INV>(e2, o2);
     v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
 }
 

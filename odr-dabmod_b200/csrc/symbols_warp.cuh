@@ -27,6 +27,7 @@ namespace dabmod {
 
 constexpr int SW_WARPS = 12;                // warps (= symbols in flight) per CTA
 constexpr int SW_THREADS = SW_WARPS * 32;
+constexpr int SW_GROUPS = 1;                // 1: all warps in step; 2: two groups half a symbol apart (measured slower)
 constexpr int SW_XPAD = 65;                 // lane stride (complex) of the exchange buffer
 constexpr int SW_N = 2048, SW_K = 1536;
 constexpr int SW_CPL = SW_K / 32;           // 48 source carriers per lane
@@ -36,6 +37,7 @@ struct SymWSmem {
     uint32_t bin_t[SW_CPL / 2 * 32];        // bin_of_src transposed, two per word: [i/2][lane] holds the FFT bins of
                                             // source carriers 48*lane + i, i even (low half) and i + 1 (high half)
     uint32_t spread[256];
+    uint32_t ph0[6 * 32];                   // phase reference of the lane's carriers, nibble packed: [word][lane]
     float2 c8[16];                          // value of phase code 0..7 (units of pi/4); code 8 = empty bin
     float2 x[SW_WARPS][32 * SW_XPAD];       // per-warp exchange buffer; its first 2048 bytes double as the
                                             // per-bin phase-code staging of the next symbol
@@ -69,6 +71,15 @@ __device__ __forceinline__ RowBits sw_load_row(const uint8_t *row, int lane)
     return b;
 }
 
+__device__ __forceinline__ void sw_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sw_bar_arrive(int id, int nthreads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <bool POST>
 __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_constant__ SymWParams pw)
 {
@@ -90,6 +101,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
         for (int n = 0; n < 8; n++) s |= ((b >> (7 - n)) & 1u) << (4 * n);
         sm.spread[b] = s;
     }
+    for (int i = tid; i < 6 * 32; i += SW_THREADS) {
+        const int w = i >> 5, l = i & 31;
+        uint32_t v = 0;
+#pragma unroll
+        for (int n = 0; n < 8; n++) v |= (uint32_t)__ldg(p.phase0 + SW_CPL * l + 8 * w + n) << (4 * n);
+        sm.ph0[i] = v;
+    }
     if (tid < 16) {
         // exactly the values the reference's float32 product chain takes:
         // {1, v, 0, -v, -1} with v = (float)M_SQRT1_2 (v*v rounds to 0.5)
@@ -99,198 +117,208 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     }
     __syncthreads();
 
-    // Persistent CTA (one per SM): round r = the SW_WARPS work items r*SW_WARPS .. +SW_WARPS-1
-    unsigned clip = 0;
-    const long long n_items = (long long)pw.n_tf * p.n_chunks;
-    const long long n_rounds = (n_items + SW_WARPS - 1) / SW_WARPS;
-    for (long long round = blockIdx.x; round < n_rounds; round += gridDim.x) {
-        // a warp beyond the last item idles through the barriers of the round
-        const long long item_raw = round * SW_WARPS + warp;
-        const bool valid = item_raw < n_items;
-        const long long item = valid ? item_raw : 0;
-        const int tf = (int)(item / p.n_chunks);
-        const int chunk = (int)(item - (long long)tf * p.n_chunks);
-        const int sym0 = chunk * p.groups_per_chunk;
-        const int sym1 = min(sym0 + p.groups_per_chunk, p.n_groups);
-        const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
-        const size_t out_base = (size_t)tf * p.tf_samples;
-        float2 *xb = sm.x[warp];
-        uint8_t *code = reinterpret_cast<uint8_t *>(xb);
+    float2 *xb = sm.x[warp];
+    uint8_t *code = reinterpret_cast<uint8_t *>(xb);
+    // The warps walk through their symbols in step (one named barrier per symbol): the loop
+    // body is ~50 KB of straight-line code, far beyond the instruction cache, and warps at
+    // different places in it would each stream it separately (measured: 1.03 ms free-running,
+    // 0.62 ms in step).  SW_GROUPS == 2 splits them into two groups half a symbol apart so
+    // that one group's store/scatter latency overlaps the other's butterflies; the second
+    // instruction stream costs more than the overlap gains (0.65 ms).
+    constexpr int GRP_THREADS = SW_THREADS / SW_GROUPS;
+    const int grp = warp / (SW_WARPS / SW_GROUPS);
+    bool first_iter = true;
 
+    // Work split: the batch is one sequence of n_tf * L transformed symbols (symbol s = 1..L of
+    // every TF; the all-zero null symbol s = 0 is written by whoever owns s = 1).  Every warp
+    // of the grid takes one contiguous range of it, so there is one phase prefix per warp
+    // and the ranges differ by at most one symbol.
+    unsigned clip = 0;
+    const int L = p.L;
+    const long long n_sym = (long long)pw.n_tf * L;
+    const long long n_warps = (long long)gridDim.x * SW_WARPS;
+    const int per_warp = (int)((n_sym + n_warps - 1) / n_warps);
+    const long long g0 = ((long long)blockIdx.x * SW_WARPS + warp) * per_warp;
+    const long long g1 = g0 + per_warp < n_sym ? g0 + per_warp : n_sym;
+
+    uint32_t ph[6] = {0, 0, 0, 0, 0, 0};
+    RowBits nextrow = {0, 0, 0, 0};
+    if (g0 < n_sym) {
+        const int tf = (int)(g0 / L);
+        const int s_first = 1 + (int)(g0 - (long long)tf * L);
+        const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
         // ---- running phase of the lane's 48 source carriers, 8 nibbles per word ----
-        uint32_t ph[6];
-    #pragma unroll
-        for (int w = 0; w < 6; w++) {
-            uint32_t v = 0;
-    #pragma unroll
-            for (int n = 0; n < 8; n++) v |= (uint32_t)__ldg(p.phase0 + SW_CPL * lane + 8 * w + n) << (4 * n);
-            ph[w] = v;
-        }
-        // Phase prefix: symbol s >= 2 carries data row d = s - 2.  Rows before the chunk are
+#pragma unroll
+        for (int w = 0; w < 6; w++) ph[w] = sm.ph0[w * 32 + lane];
+        // Phase prefix: symbol s >= 2 carries data row d = s - 2.  Rows before the range are
         // summed bit-sliced: increment = 1 + 2 (i ^ q) + 4 q (units of pi/4), so
         // sum = nd + 2 (c0 + 2 c1) + 4 pq with (c1 c0) a 2-bit counter of i^q, pq the parity of q.
-        {
-            const int nd = max(0, sym0 - 2);
-            uint32_t c0l = 0, c0h = 0, c1l = 0, c1h = 0, pql = 0, pqh = 0;
-            const uint8_t *row = bits;
-    #pragma unroll 16
-            for (int d = 0; d < nd; d++, row += K / 4) {
-                const RowBits b = sw_load_row(row, lane);
-                const uint32_t xl = b.i_lo ^ b.q_lo, xh = b.i_hi ^ b.q_hi;
-                c1l ^= c0l & xl; c1h ^= c0h & xh;
-                c0l ^= xl; c0h ^= xh;
-                pql ^= b.q_lo; pqh ^= b.q_hi;
-            }
-            const uint32_t base = (uint32_t)(nd & 7) * 0x11111111u;
-            const uint32_t m2l = c1l ^ pql, m2h = c1h ^ pqh;
-    #pragma unroll
-            for (int w = 0; w < 6; w++) {
-                const uint32_t b0 = ((w < 4 ? c0l >> (8 * w) : c0h >> (8 * (w - 4)))) & 0xffu;
-                const uint32_t b1 = ((w < 4 ? m2l >> (8 * w) : m2h >> (8 * (w - 4)))) & 0xffu;
-                const uint32_t t = (base + 2u * sm.spread[b0] + 4u * sm.spread[b1]) & 0x77777777u;
-                ph[w] = (ph[w] + t) & 0x77777777u;
-            }
+        const int nd = max(0, s_first - 2);
+        uint32_t c0l = 0, c0h = 0, c1l = 0, c1h = 0, pql = 0, pqh = 0;
+        const uint8_t *row = bits;
+#pragma unroll 16
+        for (int d = 0; d < nd; d++, row += K / 4) {
+            const RowBits b = sw_load_row(row, lane);
+            const uint32_t xl = b.i_lo ^ b.q_lo, xh = b.i_hi ^ b.q_hi;
+            c1l ^= c0l & xl; c1h ^= c0h & xh;
+            c0l ^= xl; c0h ^= xh;
+            pql ^= b.q_lo; pqh ^= b.q_hi;
         }
-
-        // bit row of the first data symbol of the chunk, then always one symbol ahead
-        RowBits nextrow = {0, 0, 0, 0};
-        {
-            const int s_first_data = max(sym0, 2);
-            if (s_first_data < sym1) nextrow = sw_load_row(bits + (size_t)(s_first_data - 2) * (K / 4), lane);
+        const uint32_t base = (uint32_t)(nd & 7) * 0x11111111u;
+        const uint32_t m2l = c1l ^ pql, m2h = c1h ^ pqh;
+#pragma unroll
+        for (int w = 0; w < 6; w++) {
+            const uint32_t b0 = ((w < 4 ? c0l >> (8 * w) : c0h >> (8 * (w - 4)))) & 0xffu;
+            const uint32_t b1 = ((w < 4 ? m2l >> (8 * w) : m2h >> (8 * (w - 4)))) & 0xffu;
+            const uint32_t t = (base + 2u * sm.spread[b0] + 4u * sm.spread[b1]) & 0x77777777u;
+            ph[w] = (ph[w] + t) & 0x77777777u;
         }
-        // The warps of a CTA walk through their chunks in step (one barrier per symbol): the
-        // loop body is ~60 KB of straight-line code, far beyond the instruction cache, and
-        // warps at different places in it would each stream it separately.
-        for (int it = 0; it < p.groups_per_chunk; it++) {
-            __syncthreads();
-            const int s = sym0 + it;
-            if (!valid || s >= sym1) continue;
-            if (s == 0) {
-                // null symbol without TII: all-zero carriers -> all-zero samples, whatever gain
-                // it borrows from symbol 1 (GainControl.cpp:139-144)
+        // bit row of the first data symbol of the range; afterwards always one symbol ahead
+        if (s_first >= 2) nextrow = sw_load_row(bits + (size_t)(s_first - 2) * (K / 4), lane);
+    }
+    {
+        for (int it = 0; it < per_warp; it++) {
+            sw_bar_sync(1 + grp, GRP_THREADS);
+            if (SW_GROUPS == 2 && first_iter && grp == 1) sw_bar_sync(3, SW_THREADS);     // wait for group 0's half-way mark
+            const long long g = g0 + it;
+            const bool fft_symbol = g < g1;
+            const int tf = fft_symbol ? (int)(g / L) : 0;
+            const int s = 1 + (int)(g - (long long)tf * L);
+            const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
+            const size_t out_base = (size_t)tf * p.tf_samples;
+            if (fft_symbol && s == 1) {
+                // start of a TF.  Null symbol without TII: all-zero carriers -> all-zero samples,
+                // whatever gain it borrows from symbol 1 (GainControl.cpp:139-144).  The
+                // differential chain restarts from the phase reference (DifferentialModulator.cpp:65).
                 for (int i = lane; i < p.null_size; i += 32)
                     store_sample<POST>(p.out, out_base + i, make_float2(0.f, 0.f), p.post, clip);
-                continue;
+#pragma unroll
+                for (int w = 0; w < 6; w++) ph[w] = sm.ph0[w * 32 + lane];
             }
-            // ---- 1. differential phase of this symbol, scattered by FFT bin as byte codes ----
-            if (s >= 2) {
+            if (fft_symbol) {
+                // ---- 1. differential phase of this symbol, scattered by FFT bin as byte codes ----
                 const RowBits b = nextrow;
-                if (s + 1 < sym1) nextrow = sw_load_row(bits + (size_t)(s - 1) * (K / 4), lane);
-    #pragma unroll
-                for (int w = 0; w < 6; w++) {
-                    const uint32_t ib = ((w < 4 ? b.i_lo >> (8 * w) : b.i_hi >> (8 * (w - 4)))) & 0xffu;
-                    const uint32_t qb = ((w < 4 ? b.q_lo >> (8 * w) : b.q_hi >> (8 * (w - 4)))) & 0xffu;
-                    ph[w] = (ph[w] + phase_step(sm.spread, ib, qb)) & 0x77777777u;
+                if (s + 1 <= L && g + 1 < g1) nextrow = sw_load_row(bits + (size_t)(s - 1) * (K / 4), lane);
+                if (s >= 2) {
+#pragma unroll
+                    for (int w = 0; w < 6; w++) {
+                        const uint32_t ib = ((w < 4 ? b.i_lo >> (8 * w) : b.i_hi >> (8 * (w - 4)))) & 0xffu;
+                        const uint32_t qb = ((w < 4 ? b.q_lo >> (8 * w) : b.q_hi >> (8 * (w - 4)))) & 0xffu;
+                        ph[w] = (ph[w] + phase_step(sm.spread, ib, qb)) & 0x77777777u;
+                    }
                 }
-            }
                 // (all table loads first: the compiler cannot tell that the byte stores below
-            // never hit the table, and would otherwise order every load behind a store)
-            uint32_t bins[SW_CPL / 2];
+                // never hit the table, and would otherwise order every load behind a store)
+                uint32_t bins[SW_CPL / 2];
 #pragma unroll
-            for (int i = 0; i < SW_CPL / 2; i++) bins[i] = sm.bin_t[i * 32 + lane];
+                for (int i = 0; i < SW_CPL / 2; i++) bins[i] = sm.bin_t[i * 32 + lane];
 #pragma unroll
-            for (int i = 0; i < SW_CPL; i++) {
-                const uint32_t c = (ph[i >> 3] >> (4 * (i & 7))) & 7u;
-                const uint32_t bin = (i & 1) ? bins[i >> 1] >> 16 : bins[i >> 1] & 0xffffu;
-                code[bin] = (uint8_t)c;
-            }
-            __syncwarp();
+                for (int i = 0; i < SW_CPL; i++) {
+                    const uint32_t c = (ph[i >> 3] >> (4 * (i & 7))) & 7u;
+                    const uint32_t bin = (i & 1) ? bins[i >> 1] >> 16 : bins[i >> 1] & 0xffffu;
+                    code[bin] = (uint8_t)c;
+                }
+                __syncwarp();
 
-            // ---- 2. inverse FFT, pass 1: lane owns bins lane + 32 r, r < 64 (radix 64) ----
-            // Bins 769..1279 and bin 0 are empty (OfdmGenerator.cpp:207-220): r in 25..39 for
-            // every lane, r = 24 except lane 0, r = 0 for lane 0.
-            float2 v[64];
-    #pragma unroll
-            for (int r = 0; r < 64; r++) {
-                if (r >= 25 && r <= 39) {
-                    v[r] = make_float2(0.f, 0.f);
+                // ---- 2. inverse FFT, pass 1: lane owns bins lane + 32 r, r < 64 (radix 64) ----
+                // Bins 769..1279 and bin 0 are empty (OfdmGenerator.cpp:207-220): r in 25..39 for
+                // every lane, r = 24 except lane 0, r = 0 for lane 0.
+                float2 v[64];
+#pragma unroll
+                for (int r = 0; r < 64; r++) {
+                    if (r >= 25 && r <= 39) {
+                        v[r] = make_float2(0.f, 0.f);
+                    }
+                    else {
+                        uint32_t c = code[lane + 32 * r];
+                        if (r == 0 && lane == 0) c = 8;
+                        if (r == 24 && lane != 0) c = 8;
+                        v[r] = sm.c8[c];
+                    }
+                }
+                fft64<true>(v);
+                __syncwarp();                        // all codes read before the buffer is overwritten
+#pragma unroll
+                for (int r = 0; r < 64; r++) xb[lane * SW_XPAD + r] = v[r];
+                __syncwarp();
+            }
+            if (SW_GROUPS == 2 && first_iter && grp == 0) sw_bar_arrive(3, SW_THREADS);   // half-way mark of the first symbol
+            first_iter = false;
+            if (fft_symbol) {
+                // ---- pass 2: butterflies j = lane and lane + 32 (radix 32), sample n = j + 64 r ----
+                // y[i] = sample lane + 32 i
+                float2 y[64];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = lane + 32 * h;
+                    float2 u[32];
+#pragma unroll
+                    for (int r = 0; r < 32; r++) u[r] = xb[r * SW_XPAD + j];
+#pragma unroll
+                    for (int r = 1; r < 32; r++) u[r] = cmul(u[r], sm.tw[(r - 1) * 64 + j]);
+                    fft32<true>(u);
+#pragma unroll
+                    for (int r = 0; r < 32; r++) y[2 * r + h] = u[r];
+                }
+                __syncwarp();                        // buffer free for the next symbol's codes
+
+                // ---- 3. gain (GainControl.cpp:196-340), statistics over the N samples ----
+                float g_sym;
+                if (p.gain_mode == 0) {
+                    g_sym = 512.0f;
+                }
+                else if (p.gain_mode == 1) {
+                    float mn = y[0].x, mx = y[0].x;
+#pragma unroll
+                    for (int i = 0; i < 64; i++) {
+                        mn = fminf(mn, fminf(y[i].x, y[i].y));
+                        mx = fmaxf(mx, fmaxf(y[i].x, y[i].y));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    }
+                    const float m = fmaxf(-mn, mx);
+                    g_sym = ((int)m != 0) ? 32767.0f / m : 1.0f;
                 }
                 else {
-                    uint32_t c = code[lane + 32 * r];
-                    if (r == 0 && lane == 0) c = 8;
-                    if (r == 24 && lane != 0) c = 8;
-                    v[r] = sm.c8[c];
+                    // two-pass mean / variance of re and im separately (packed: .x = re, .y = im)
+                    float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 64; i++) sum = cadd(sum, y[i]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+                        sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+                    }
+                    const float2 mean = make_float2(sum.x * (1.0f / N), sum.y * (1.0f / N));
+                    float2 var = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 64; i++) {
+                        const float2 d = csub(y[i], mean);
+                        var = __ffma2_rn(d, d, var);
+                    }
+                    float vr = var.x, vi = var.y;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        vr += __shfl_xor_sync(0xffffffffu, vr, o);
+                        vi += __shfl_xor_sync(0xffffffffu, vi, o);
+                    }
+                    const float sdr = p.var_factor * sqrtf(vr * (1.0f / N));
+                    const float sdi = p.var_factor * sqrtf(vi * (1.0f / N));
+                    // NULL detection looks at the real part only (GainControl.cpp:331)
+                    g_sym = ((int)sdr != 0) ? 32767.0f / fmaxf(sdr, sdi) : 1.0f;
                 }
-            }
-            fft64<true>(v);
-            __syncwarp();                        // all codes read before the buffer is overwritten
-    #pragma unroll
-            for (int r = 0; r < 64; r++) xb[lane * SW_XPAD + r] = v[r];
-            __syncwarp();
-            // ---- pass 2: butterflies j = lane and lane + 32 (radix 32), sample n = j + 64 r ----
-            // y[i] = sample lane + 32 i
-            float2 y[64];
-    #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int j = lane + 32 * h;
-                float2 u[32];
-    #pragma unroll
-                for (int r = 0; r < 32; r++) u[r] = xb[r * SW_XPAD + j];
-    #pragma unroll
-                for (int r = 1; r < 32; r++) u[r] = cmul(u[r], sm.tw[(r - 1) * 64 + j]);
-                fft32<true>(u);
-    #pragma unroll
-                for (int r = 0; r < 32; r++) y[2 * r + h] = u[r];
-            }
-            __syncwarp();                        // buffer free for the next symbol's codes
+                g_sym *= p.gain_const;
 
-            // ---- 3. gain (GainControl.cpp:196-340), statistics over the N samples ----
-            float g_sym;
-            if (p.gain_mode == 0) {
-                g_sym = 512.0f;
-            }
-            else if (p.gain_mode == 1) {
-                float mn = y[0].x, mx = y[0].x;
-    #pragma unroll
-                for (int i = 0; i < 64; i++) {
-                    mn = fminf(mn, fminf(y[i].x, y[i].y));
-                    mx = fmaxf(mx, fmaxf(y[i].x, y[i].y));
-                }
-    #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                }
-                const float m = fmaxf(-mn, mx);
-                g_sym = ((int)m != 0) ? 32767.0f / m : 1.0f;
-            }
-            else {
-                // two-pass mean / variance of re and im separately
-                float sr = 0.f, si = 0.f;
-    #pragma unroll
-                for (int i = 0; i < 64; i++) { sr += y[i].x; si += y[i].y; }
-    #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    sr += __shfl_xor_sync(0xffffffffu, sr, o);
-                    si += __shfl_xor_sync(0xffffffffu, si, o);
-                }
-                const float mr = sr * (1.0f / N), mi = si * (1.0f / N);
-                float vr = 0.f, vi = 0.f;
-    #pragma unroll
-                for (int i = 0; i < 64; i++) {
-                    const float dr = y[i].x - mr, di = y[i].y - mi;
-                    vr = fmaf(dr, dr, vr); vi = fmaf(di, di, vi);
-                }
-    #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    vr += __shfl_xor_sync(0xffffffffu, vr, o);
-                    vi += __shfl_xor_sync(0xffffffffu, vi, o);
-                }
-                const float sdr = p.var_factor * sqrtf(vr * (1.0f / N));
-                const float sdi = p.var_factor * sqrtf(vi * (1.0f / N));
-                // NULL detection looks at the real part only (GainControl.cpp:331)
-                g_sym = ((int)sdr != 0) ? 32767.0f / fmaxf(sdr, sdi) : 1.0f;
-            }
-            g_sym *= p.gain_const;
-
-            // ---- 4. guard interval + store (GuardIntervalInserter.cpp:301-319) ----
-            {
+                // ---- 4. guard interval + store (GuardIntervalInserter.cpp:301-319) ----
                 const int pre = p.sym_size - N;
                 const size_t pos = out_base + sym_pos(p, s);
-    #pragma unroll
+#pragma unroll
                 for (int i = 0; i < 64; i++) {
                     const int n = lane + 32 * i;
-                    const float2 o = make_float2(y[i].x * g_sym, y[i].y * g_sym);
+                    const float2 o = cscale(y[i], g_sym);
                     store_sample<POST>(p.out, pos + pre + n, o, p.post, clip);
                     if (n >= N - pre) store_sample<POST>(p.out, pos + n - (N - pre), o, p.post, clip);
                 }
