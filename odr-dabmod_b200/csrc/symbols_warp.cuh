@@ -32,16 +32,22 @@ constexpr int SW_XPAD = 65;                 // lane stride (complex) of the exch
 constexpr int SW_N = 2048, SW_K = 1536;
 constexpr int SW_CPL = SW_K / 32;           // 48 source carriers per lane
 
+constexpr int SW_CODES = SW_K;              // one phase code per occupied bin (the 512 guard-band bins are skipped)
+
 struct SymWSmem {
-    float2 tw[31 * 64];                     // second pass twiddles: tw[(r-1)*64 + j] = e^{+j 2 pi j r / 2048}
-    uint32_t bin_t[SW_CPL / 2 * 32];        // bin_of_src transposed, two per word: [i/2][lane] holds the FFT bins of
-                                            // source carriers 48*lane + i, i even (low half) and i + 1 (high half)
+    float2 tw[31 * 32];                     // second pass twiddles: tw[(r-1)*32 + j] = e^{+j 2 pi j r / 2048}, j < 32
+                                            // (j + 32: times the constants W64^r, fft_reg.cuh mul_w64_ramp)
+    uint32_t bin_t[SW_CPL / 2 * 32];        // code index of the lane's source carriers, two per word: [i/2][lane]
+                                            // holds carriers 48*lane + i (low half) and i + 1 (high half);
+                                            // code index = bin - 1 (bins 1..768), bin - 512 (bins 1280..2047)
     uint32_t spread[256];
     uint32_t ph0[6 * 32];                   // phase reference of the lane's carriers, nibble packed: [word][lane]
     float2 c8[16];                          // value of phase code 0..7 (units of pi/4); code 8 = empty bin
-    float2 x[SW_WARPS][32 * SW_XPAD];       // per-warp exchange buffer; its first 2048 bytes double as the
-                                            // per-bin phase-code staging of the next symbol
+    float2 x[SW_WARPS][32 * SW_XPAD];       // per-warp exchange buffer between the two FFT passes, then the
+                                            // staging area the symbol is bulk-copied to HBM from
+    uint8_t code[SW_WARPS][SW_CODES];       // per-warp phase codes of the symbol being assembled
 };
+static_assert(sizeof(SymWSmem) <= 227 * 1024, "k_symbols_w shared memory");
 
 struct SymWParams {
     SymParams s;                            // shared with k_symbols
@@ -80,6 +86,14 @@ __device__ __forceinline__ void sw_bar_arrive(int id, int nthreads)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// shared -> global bulk async copy (cp.async.bulk, SASS UBLKCP); addresses and size multiples of 16
+__device__ __forceinline__ void sw_bulk_store(void *gdst, const void *ssrc, int bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+
 template <bool POST>
 __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_constant__ SymWParams pw)
 {
@@ -90,10 +104,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- per-CTA tables ----
-    for (int i = tid; i < 31 * 64; i += SW_THREADS) sm.tw[i] = __ldg(pw.twiddle_w + i);
+    for (int i = tid; i < 31 * 32; i += SW_THREADS) {
+        const int r1 = i >> 5, j = i & 31;
+        sm.tw[i] = __ldg(pw.twiddle_w + r1 * 64 + j);
+    }
     for (int i = tid; i < K / 2; i += SW_THREADS) {
         const int l = i / (SW_CPL / 2), c = i - l * (SW_CPL / 2);
-        sm.bin_t[c * 32 + l] = __ldg(reinterpret_cast<const uint32_t *>(p.bin_of_src) + i);
+        const uint32_t two = __ldg(reinterpret_cast<const uint32_t *>(p.bin_of_src) + i);
+        const uint32_t b0 = two & 0xffffu, b1 = two >> 16;
+        sm.bin_t[c * 32 + l] = (b0 < 1024 ? b0 - 1 : b0 - 512) | ((b1 < 1024 ? b1 - 1 : b1 - 512) << 16);
     }
     for (int b = tid; b < 256; b += SW_THREADS) {
         uint32_t s = 0;
@@ -118,7 +137,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     __syncthreads();
 
     float2 *xb = sm.x[warp];
-    uint8_t *code = reinterpret_cast<uint8_t *>(xb);
+    uint8_t *code = sm.code[warp];
     // The warps walk through their symbols in step (one named barrier per symbol): the loop
     // body is ~50 KB of straight-line code, far beyond the instruction cache, and warps at
     // different places in it would each stream it separately (measured: 1.03 ms free-running,
@@ -230,14 +249,18 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                         v[r] = make_float2(0.f, 0.f);
                     }
                     else {
-                        uint32_t c = code[lane + 32 * r];
+                        uint32_t c = code[r == 0 ? max(lane - 1, 0) : r < 25 ? lane + 32 * r - 1 : lane + 32 * (r - 16)];
                         if (r == 0 && lane == 0) c = 8;
                         if (r == 24 && lane != 0) c = 8;
                         v[r] = sm.c8[c];
                     }
                 }
                 fft64<true>(v);
-                __syncwarp();                        // all codes read before the buffer is overwritten
+                // the previous symbol's bulk copies must have read the staging area by now
+                if (!POST) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int r = 0; r < 64; r++) xb[lane * SW_XPAD + r] = v[r];
                 __syncwarp();
@@ -255,12 +278,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
 #pragma unroll
                     for (int r = 0; r < 32; r++) u[r] = xb[r * SW_XPAD + j];
 #pragma unroll
-                    for (int r = 1; r < 32; r++) u[r] = cmul(u[r], sm.tw[(r - 1) * 64 + j]);
+                    for (int r = 1; r < 32; r++) u[r] = cmul(u[r], sm.tw[(r - 1) * 32 + lane]);
+                    if (h == 1) mul_w64_ramp<true>(u);
                     fft32<true>(u);
 #pragma unroll
                     for (int r = 0; r < 32; r++) y[2 * r + h] = u[r];
                 }
-                __syncwarp();                        // buffer free for the next symbol's codes
+                __syncwarp();                        // exchange buffer read by every lane: free for the staging
 
                 // ---- 3. gain (GainControl.cpp:196-340), statistics over the N samples ----
                 float g_sym;
@@ -315,15 +339,37 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                 // ---- 4. guard interval + store (GuardIntervalInserter.cpp:301-319) ----
                 const int pre = p.sym_size - N;
                 const size_t pos = out_base + sym_pos(p, s);
+                if (POST) {
 #pragma unroll
-                for (int i = 0; i < 64; i++) {
-                    const int n = lane + 32 * i;
-                    const float2 o = cscale(y[i], g_sym);
-                    store_sample<POST>(p.out, pos + pre + n, o, p.post, clip);
-                    if (n >= N - pre) store_sample<POST>(p.out, pos + n - (N - pre), o, p.post, clip);
+                    for (int i = 0; i < 64; i++) {
+                        const int n = lane + 32 * i;
+                        const float2 o = cscale(y[i], g_sym);
+                        store_sample<POST>(p.out, pos + pre + n, o, p.post, clip);
+                        if (n >= N - pre) store_sample<POST>(p.out, pos + n - (N - pre), o, p.post, clip);
+                    }
+                }
+                else {
+                    // complexf output: the scaled symbol goes to shared memory in natural order and
+                    // two bulk async copies (TMA engine) land it in HBM, body and cyclic prefix;
+                    // the LSU sees 64 conflict-free shared stores instead of 79 global ones and
+                    // nobody waits for the memory system.
+#pragma unroll
+                    for (int i = 0; i < 64; i++) xb[lane + 32 * i] = cscale(y[i], g_sym);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        float2 *gout = reinterpret_cast<float2 *>(p.out) + pos;
+                        sw_bulk_store(gout + pre, xb, N * (int)sizeof(float2));
+                        sw_bulk_store(gout, xb + (N - pre), pre * (int)sizeof(float2));
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
             }
         }
+    }
+    if (!POST) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
     }
     if (POST && p.post.format != 0) flush_clip(p.post, clip);
 }
