@@ -194,6 +194,77 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+POLY = [1.0, 0.05, -0.02, 0.003, 0.0, 0.0, 0.1, -0.05, 0.01, 0.0]   # 5 + 5 odd-polynomial terms (config 3)
+# algorithmic bytes / flops per TM I TF of the resampling stages
+RES_INFO = {
+    8192000: {"out_samples": 786432, "flop": 133.7e6},
+    10000000: {"out_samples": 960000, "flop": 160.6e6},
+}
+ETI_PER_TF_MODE = {1: 4, 2: 1, 3: 1, 4: 2}
+
+
+def other_configs():
+    """The BASELINE.json configs that are not the headline workload (device-resident only)."""
+    return [
+        ("c1 TM I native, no FIR", dict(mode=1), 1024),
+        ("c3 TM I FIR + resample 8.192 Msps + poly(5)", dict(mode=1, fir_taps="default", output_rate=8192000,
+                                                             normalise=1.0 / 46000.0, poly=POLY), 256),
+        ("c5 TM I FIR + resample 10 Msps + poly(5), one GPU's share", dict(mode=1, fir_taps="default",
+                                                                           output_rate=10000000,
+                                                                           normalise=1.0 / 46000.0, poly=POLY), 128),
+        ("c3s TM I FIR + resample 8.192 Msps + poly(5), s16 out", dict(mode=1, fir_taps="default", output_rate=8192000,
+                                                                       normalise=1.0 / 46000.0, poly=POLY, fmt="s16"), 256),
+        ("c4 TM II native", dict(mode=2), 4096),
+        ("c4 TM III native", dict(mode=3), 4096),
+        ("c4 TM IV native", dict(mode=4), 2048),
+    ]
+
+
+def measure_config(dm, torch, name, kw, n_tf, stream, peak, steps=5, warmup=3):
+    """Device-resident throughput and per-kernel times of one configuration."""
+    mod = dm.Modulator(max_batch=n_tf, **kw)
+    g = torch.Generator(device="cpu").manual_seed(4321)
+    bits = torch.randint(0, 256, (n_tf, mod.tf_in_bytes), dtype=torch.uint8, generator=g).to("cuda")
+    out = torch.empty(n_tf * mod.tf_out_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(warmup):
+        mod.process_batch_device(bits.data_ptr(), n_tf, out.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        mod.process_batch_device(bits.data_ptr(), n_tf, out.data_ptr(), stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    mod.set_param("profile", 1)
+    kt = {}
+    for _ in range(3):
+        mod.process_batch_device(bits.data_ptr(), n_tf, out.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        for k, t in mod.kernel_times():
+            kt.setdefault(k, []).append(t)
+    mode = kw.get("mode", 1)
+    res = {"workload": name, "tfs_per_step": n_tf, "ms_per_step": ms,
+           "eti_frames_per_s": n_tf * ETI_PER_TF_MODE[mode] / (ms * 1e-3),
+           "out_bytes_per_step": n_tf * mod.tf_out_bytes,
+           "kernels_ms": {k: float(np.mean(v)) for k, v in kt.items()}}
+    rate = kw.get("output_rate", 2048000)
+    if rate in RES_INFO and mode == 1:
+        k = [x for x in kt if x.startswith("k_resample")][0]
+        t = float(np.mean(kt[k])) * 1e-3
+        info = RES_INFO[rate]
+        byt = n_tf * (TF_SAMPLES * 8 + info["out_samples"] * (mod.tf_out_bytes // mod.tf_out_samples))
+        res["resampler"] = {"kernel": k, "ms": t * 1e3, "algorithmic_GB/s": byt / t / 1e9,
+                            "frac_of_hbm_peak": byt / t / 1e9 / peak,
+                            "algorithmic_TFLOP/s_fp32": n_tf * info["flop"] / t / 1e12,
+                            "note": "FP32-bound stage (17-19 flop/B > the 11 flop/B ridge): see DESIGN.md"}
+    mod.close()
+    del bits, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def gpu_arm(args):
     import torch
     import dabmod_loader
@@ -215,6 +286,15 @@ def gpu_arm(args):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.only:
+        # development aid: one of the other_configs by prefix, device-resident, no headline line
+        stream = torch.cuda.Stream()
+        peak, _ = measured_peaks()
+        for name, kw, ntf in other_configs():
+            if name.startswith(args.only):
+                print(json.dumps(measure_config(dm, torch, name, kw, ntf, stream, peak, steps=args.steps)))
+        return 0
 
     n_tf = TFS_PER_STEP
     mod = dm.Modulator(mode=MODE, fir_taps="default", max_batch=n_tf, device=local_rank)
@@ -320,6 +400,15 @@ def gpu_arm(args):
         cpu = {"value": v, "unit": "ETI frames/s", "cores": cores, "kind": kind,
                "sample": "%d TFs per thread x %d threads, %.1f s (same TM I + FIR default taps chain)" % (tfs, cores, dt_cpu)}
 
+    others = None
+    if world == 1 and not args.no_extras:
+        others = []
+        for name, kw, ntf in other_configs():
+            try:
+                others.append(measure_config(dm, torch, name, kw, ntf, stream, peak))
+            except Exception as e:                       # an extra must never cost the headline line
+                others.append({"workload": name, "error": str(e)})
+
     line = {
         "metric": METRIC, "value": value, "unit": "ETI frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -338,6 +427,8 @@ def gpu_arm(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if others is not None:
+        line["other_configs"] = others
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -351,6 +442,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only", default="", help="development: measure only the other_configs entry with this prefix")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (other_configs key)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "resample.cuh"
+#include "resample_up.cuh"
 #include "symbols_warp.cuh"
 #include "tables.h"
 
@@ -128,6 +129,8 @@ struct dabmod_b200 {
     DevBuf<float2> d_hist;         // last Ni input samples of the stream (zeros at stream start)
     DevBuf<float2> d_scratch;
     int res_grid = 0;
+    bool res_up = false;           // k_resample_up applies (Ni = 4096, integer ratio <= 4)
+    bool allow_res_up = true;      // "res_kernel" knob: 0 = always the generic kernel
     size_t res_smem = 0;
 
     uint64_t clipped_last = 0;
@@ -432,6 +435,28 @@ void enqueue_resampler(dabmod_b200 *h, const float2 *in, size_t n_tf, void *d_ou
     p.scratch = h->res_smem ? nullptr : h->d_scratch.p;
     p.out = d_out;
     p.post = make_post(h, post);
+    if (h->res_up && h->allow_res_up) {
+        // TM I, integer up-sampling: L transforms of Ni points per hop, all in shared memory
+        RuParams pu{};
+        pu.r = p;
+        pu.L = (int)rp.L;
+        const int grid = (int)std::min<long long>((p.total_hops + RU_TEAMS - 1) / RU_TEAMS, h->sm_count);
+        ProfScope prof(h, "k_resample_up", s);
+        if (post) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_resample_up<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(RuSmem)));
+            k_resample_up<true><<<grid, RU_THREADS, sizeof(RuSmem), s>>>(pu);
+        }
+        else {
+            CUDA_CHECK(cudaFuncSetAttribute(k_resample_up<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(RuSmem)));
+            k_resample_up<false><<<grid, RU_THREADS, sizeof(RuSmem), s>>>(pu);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        prof.end();
+        launches++;
+    }
+    else {
     const int grid = (int)std::min<long long>(p.total_hops, h->res_grid);
     ProfScope prof(h, "k_resample", s);
     if (post) {
@@ -447,6 +472,7 @@ void enqueue_resampler(dabmod_b200 *h, const float2 *in, size_t n_tf, void *d_ou
     CUDA_CHECK(cudaGetLastError());
     prof.end();
     launches++;
+    }
     // stream state for the next launch: the last Ni input samples (Resampler.cpp:143-145,185-191)
     const size_t total = n_tf * (size_t)h->m.tf_samples;
     CUDA_CHECK(cudaMemcpyAsync(h->d_hist.p, in + total - rp.ni, sizeof(float2) * rp.ni, cudaMemcpyDeviceToDevice, s));
@@ -614,6 +640,7 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
                                "Resampler: FFT size " + std::to_string(rp.no) + " has a prime factor above 7");
             h->rp = rp;
             h->has_res = true;
+            h->res_up = rp.ni == RU_NI && rp.M == 1 && rp.L >= 2 && rp.L <= (uint64_t)RU_MAX_L;
             h->d_res_win.upload(resampler_window(rp.ni), h->s_compute);
             std::vector<float> t;
             twiddle_table(rp.ni, t);
@@ -835,6 +862,7 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             else if (n == "profile") { int v; ss >> v; h->profile = v != 0; }
             else if (n == "sym_chunks") { int v; ss >> v; h->force_chunks = v < 0 ? 0 : v; }
             else if (n == "sym_kernel") { int v; ss >> v; h->use_warp_kernel = v != 0; }
+            else if (n == "res_kernel") { int v; ss >> v; h->allow_res_up = v != 0; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {
                 std::string v; ss >> v;

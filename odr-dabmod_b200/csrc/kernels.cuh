@@ -31,24 +31,22 @@ struct PostParams {
 __device__ __forceinline__ float2 dpd_apply(const PostParams &pp, float2 x)
 {
     if (pp.dpd_mode == 1) {
-        // __fmul_rn/__fadd_rn keep the reference's operation order free of FMA contraction
-        const float mag = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+        // Horner steps as fused multiply-adds (the reference is built with GCC's default
+        // -ffp-contract=fast on an FMA machine, so neither rounding is canonical)
+        const float mag = fmaf(x.x, x.x, x.y * x.y);
         float amp = pp.am[4];
         float ph = pp.pm[4];
 #pragma unroll
         for (int i = 3; i >= 0; i--) {
-            amp = __fadd_rn(pp.am[i], __fmul_rn(mag, amp));
-            ph = __fadd_rn(pp.pm[i], __fmul_rn(mag, ph));
+            amp = fmaf(mag, amp, pp.am[i]);
+            ph = fmaf(mag, ph, pp.pm[i]);
         }
         ph = -ph;
-        const float p2 = __fmul_rn(ph, ph);
-        const float re = __fsub_rn(1.0f, __fmul_rn(p2, __fadd_rn(-0.5f, __fmul_rn(p2,
-                         __fadd_rn(0.486666f, __fmul_rn(p2, -0.00138888f))))));
-        const float im = __fmul_rn(ph, __fadd_rn(1.0f, __fmul_rn(p2,
-                         __fadd_rn(0.166666f, __fmul_rn(p2, 0.00833333f)))));
-        const float ar = __fmul_rn(x.x, amp), ai = __fmul_rn(x.y, amp);
-        return make_float2(__fsub_rn(__fmul_rn(ar, re), __fmul_rn(ai, im)),
-                           __fadd_rn(__fmul_rn(ar, im), __fmul_rn(ai, re)));
+        const float p2 = ph * ph;
+        const float re = fmaf(-p2, fmaf(p2, fmaf(p2, -0.00138888f, 0.486666f), -0.5f), 1.0f);
+        const float im = ph * fmaf(p2, fmaf(p2, 0.00833333f, 0.166666f), 1.0f);
+        const float ar = x.x * amp, ai = x.y * amp;
+        return make_float2(fmaf(ar, re, -ai * im), fmaf(ar, im, ai * re));
     }
     if (pp.dpd_mode == 2) {
         const float mag = hypotf(x.x, x.y);

@@ -58,23 +58,36 @@ struct SymWParams {
 // I/Q bit bytes of the lane's 48 carriers in one bit row: 6 bytes each, as (4 bytes, 2 bytes)
 struct RowBits { uint32_t i_lo, i_hi, q_lo, q_hi; };
 
-// The lane's 6 bytes start at byte 6*lane (2-byte aligned): two aligned 32-bit loads cover them.
-__device__ __forceinline__ void sw_load6(const uint8_t *p6, uint32_t &lo, uint32_t &hi)
+// The lane's 6 bytes of a bit row start at byte 6*lane (2-byte aligned): two aligned 32-bit
+// loads cover them.  Loading (RowRaw) and unpacking (RowBits) are separate so that a row
+// can be fetched one symbol ahead without anything waiting on the load.
+struct RowRaw { uint32_t i0, i1, q0, q1; };
+
+__device__ __forceinline__ RowRaw sw_fetch_row(const uint8_t *row, int lane)
 {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p6);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1);
-    const unsigned sh = (unsigned)(a & 2) * 8;
-    lo = __funnelshift_r(w0, w1, sh);
-    hi = (w1 >> sh) & 0xffffu;
+    const uintptr_t ai = reinterpret_cast<uintptr_t>(row + 6 * lane);
+    const uint32_t *wi = reinterpret_cast<const uint32_t *>(ai & ~(uintptr_t)3);
+    const uint32_t *wq = wi + SW_K / 32;           // the Q half starts K/8 = 192 bytes later
+    RowRaw r;
+    r.i0 = __ldg(wi); r.i1 = __ldg(wi + 1);
+    r.q0 = __ldg(wq); r.q1 = __ldg(wq + 1);
+    return r;
+}
+
+__device__ __forceinline__ RowBits sw_unpack_row(const RowRaw &r, int lane)
+{
+    const unsigned sh = (unsigned)((6 * lane) & 2) * 8;    // rows are 4-byte aligned
+    RowBits b;
+    b.i_lo = __funnelshift_r(r.i0, r.i1, sh);
+    b.i_hi = (r.i1 >> sh) & 0xffffu;
+    b.q_lo = __funnelshift_r(r.q0, r.q1, sh);
+    b.q_hi = (r.q1 >> sh) & 0xffffu;
+    return b;
 }
 
 __device__ __forceinline__ RowBits sw_load_row(const uint8_t *row, int lane)
 {
-    RowBits b;
-    sw_load6(row + 6 * lane, b.i_lo, b.i_hi);
-    sw_load6(row + SW_K / 8 + 6 * lane, b.q_lo, b.q_hi);
-    return b;
+    return sw_unpack_row(sw_fetch_row(row, lane), lane);
 }
 
 __device__ __forceinline__ void sw_bar_sync(int id, int nthreads)
@@ -161,7 +174,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     const long long g1 = g0 + per_warp < n_sym ? g0 + per_warp : n_sym;
 
     uint32_t ph[6] = {0, 0, 0, 0, 0, 0};
-    RowBits nextrow = {0, 0, 0, 0};
+    RowRaw nextrow = {0, 0, 0, 0};
     if (g0 < n_sym) {
         const int tf = (int)(g0 / L);
         const int s_first = 1 + (int)(g0 - (long long)tf * L);
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
             ph[w] = (ph[w] + t) & 0x77777777u;
         }
         // bit row of the first data symbol of the range; afterwards always one symbol ahead
-        if (s_first >= 2) nextrow = sw_load_row(bits + (size_t)(s_first - 2) * (K / 4), lane);
+        if (s_first >= 2) nextrow = sw_fetch_row(bits + (size_t)(s_first - 2) * (K / 4), lane);
     }
     {
         for (int it = 0; it < per_warp; it++) {
@@ -216,8 +229,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
             }
             if (fft_symbol) {
                 // ---- 1. differential phase of this symbol, scattered by FFT bin as byte codes ----
-                const RowBits b = nextrow;
-                if (s + 1 <= L && g + 1 < g1) nextrow = sw_load_row(bits + (size_t)(s - 1) * (K / 4), lane);
+                const RowBits b = sw_unpack_row(nextrow, lane);
+                if (s + 1 <= L && g + 1 < g1) nextrow = sw_fetch_row(bits + (size_t)(s - 1) * (K / 4), lane);
                 if (s >= 2) {
 #pragma unroll
                     for (int w = 0; w < 6; w++) {

@@ -8,5 +8,6 @@ import json
 d=json.load(open("gpurun_out/bench_$TAG.json"))
 print("value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"])
 for k,v in d["roofline"]["all_kernels"].items(): print(k, v)
+for o in d.get("other_configs") or []: print(o)
 PY
 tail -5 gpurun_out/bench.err
