@@ -364,7 +364,7 @@ def gpu_arm(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_s = float(dt.item())
     clocks = sampler.stop() if rank == 0 else None
-    checksum = int(host_out[:4096].to(torch.int64).sum().item())  # the D2H result is read
+    checksum = int(host_out[::65537].to(torch.int64).sum().item())  # the D2H result is read (strided over the whole buffer)
 
     if rank != 0:
         if dist is not None:

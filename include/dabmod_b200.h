@@ -179,6 +179,72 @@ int dabmod_b200_resampler_sizes(uint64_t in_rate, uint64_t out_rate, int resolut
 /* Thread-local description of the last error. Never NULL. */
 const char *dabmod_b200_last_error(void);
 
+/* The handle's device-resident output buffer (max_batch TFs in the output format); what
+ * dabmod_b200_process_batch copies to the host.  For callers that chain device work. */
+void *dabmod_b200_device_out(dabmod_b200 *h);
+
+/* ======================================================================================
+ * Row N1 of SURVEY.md section 8(f): the channel coding ahead of the path, i.e. the part of
+ * DabModulator's graph between EtiReader and QpskSymbolMapper (src/DabModulator.cpp:131-150,
+ * 286-383): PrbsGenerator -> ConvEncoder -> PuncturingEncoder [-> TimeInterleaver] for the FIC
+ * and every subchannel, FrameMultiplexer, BlockPartitioner.  Input: raw ETI(NI) frames of 6144
+ * bytes (what InputFileReader hands to EtiReader::loadEtiData, src/EtiReader.cpp:93-284);
+ * output: the per-TF byte blocks dabmod_b200_process* consume.
+ * ====================================================================================== */
+
+/* PuncturingRule(length in encoder-output bytes, 32-bit keep mask), src/PuncturingRule.h */
+typedef struct dabmod_b200_punct_rule {
+    uint32_t length;
+    uint32_t pattern;
+} dabmod_b200_punct_rule;
+
+/* One coded stream: [0] is the FIC (FicSource), [1..] the subchannels in STC order
+ * (SubchannelSource).  The tail rule (3, 0xcccccc) of DabModulator.cpp:316,373 is implied. */
+typedef struct dabmod_b200_stream {
+    uint32_t framesize;   /* input bytes per ETI frame: FicSource::getFramesize / SubchannelSource::framesize */
+    uint32_t out_bytes;   /* FIC: 288 (TM III: 384); subchannel: framesizeCu() * 8 */
+    uint32_t start_cu;    /* SubchannelSource::startAddress (ignored for the FIC) */
+    uint32_t n_rules;     /* 1..8 */
+    dabmod_b200_punct_rule rules[8];   /* get_rules() */
+} dabmod_b200_stream;
+
+typedef struct dabmod_b200_coder dabmod_b200_coder;
+
+/* Host-only: what EtiReader + FicSource + SubchannelSource derive from the header of one
+ * ETI(NI) frame (EtiReader.cpp:120-190, FicSource.cpp:40-63, SubchannelSource.cpp:66-170,
+ * :665-760).  EEP-A/B profiles are derived here; a UEP (short form) subchannel returns
+ * DABMOD_B200_EUNSUPPORTED -- pass its rules explicitly (the C++ adapter has them from
+ * SubchannelSource::get_rules()).  *mode = transmission mode 1..4 from MID. */
+int dabmod_b200_eti_describe(const uint8_t *frame, size_t len, int *mode, dabmod_b200_stream *streams, int cap,
+                             int *n_streams);
+
+/* One multiplex configuration on one GPU; max_frames = largest n_frames of a call. */
+int dabmod_b200_coder_create(int device, int mode, const dabmod_b200_stream *streams, int n_streams,
+                             int max_frames, dabmod_b200_coder **out);
+void dabmod_b200_coder_destroy(dabmod_b200_coder *c);
+size_t dabmod_b200_coder_tf_bytes(const dabmod_b200_coder *c);
+int dabmod_b200_coder_frames_per_tf(const dabmod_b200_coder *c);   /* BlockPartitioner d_cifCount */
+
+/* n_frames consecutive ETI frames (a multiple of frames_per_tf) -> n_frames / frames_per_tf blocks.
+ * Host buffers; synchronous. */
+int dabmod_b200_coder_process(dabmod_b200_coder *c, const uint8_t *eti_frames, size_t n_frames, uint8_t *bits_out,
+                              size_t cap, size_t *out_bytes);
+/* Same with device buffers, enqueued on `stream` (NULL = the coder's own), not synchronised. */
+int dabmod_b200_coder_process_device(dabmod_b200_coder *c, const uint8_t *d_eti_frames, size_t n_frames,
+                                     uint8_t *d_bits_out, void *stream);
+/* Forget / set the time interleaver history (TimeInterleaver.cpp:39-41: 16 frames).  For a
+ * stream sharded by frame ranges, prime with the (up to) 15 ETI frames before the shard. */
+int dabmod_b200_coder_reset(dabmod_b200_coder *c);
+int dabmod_b200_coder_prime(dabmod_b200_coder *c, const uint8_t *eti_frames, size_t n_frames);
+
+/* ETI bytes in, I/Q out: coder and modulator chained on the device (the coded blocks never
+ * travel to the host).  Both handles must be on the same device and transmission mode. */
+int dabmod_b200_process_eti_batch(dabmod_b200 *h, dabmod_b200_coder *c, const uint8_t *eti_frames, size_t n_frames,
+                                  void *iq_out, size_t cap, size_t *out_bytes);
+
+/* Thread-local description of the last coder error. Never NULL. */
+const char *dabmod_b200_coder_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,12 @@ EXPORTS = [
     "dabmod_b200_num_clipped_samples", "dabmod_b200_last_launch_count", "dabmod_b200_last_error",
     "dabmod_b200_table_interleaver", "dabmod_b200_table_phase_ref", "dabmod_b200_table_tii",
     "dabmod_b200_table_cic", "dabmod_b200_resampler_sizes", "dabmod_b200_kernel_time",
+    "dabmod_b200_device_out",
+    # row N1: channel coding
+    "dabmod_b200_eti_describe", "dabmod_b200_coder_create", "dabmod_b200_coder_destroy",
+    "dabmod_b200_coder_tf_bytes", "dabmod_b200_coder_frames_per_tf", "dabmod_b200_coder_process",
+    "dabmod_b200_coder_process_device", "dabmod_b200_coder_reset", "dabmod_b200_coder_prime",
+    "dabmod_b200_process_eti_batch", "dabmod_b200_coder_last_error",
 ]
 
 
@@ -63,6 +69,20 @@ class Config(ctypes.Structure):
         ("format", ctypes.c_int32),
         ("max_batch", ctypes.c_int32),
     ]
+
+
+class Rule(ctypes.Structure):
+    _fields_ = [("length", ctypes.c_uint32), ("pattern", ctypes.c_uint32)]
+
+
+class Stream(ctypes.Structure):
+    """dabmod_b200_stream"""
+    _fields_ = [("framesize", ctypes.c_uint32), ("out_bytes", ctypes.c_uint32), ("start_cu", ctypes.c_uint32),
+                ("n_rules", ctypes.c_uint32), ("rules", Rule * 8)]
+
+    def as_tuple(self):
+        return (self.framesize, self.out_bytes, self.start_cu,
+                tuple((self.rules[i].length, self.rules[i].pattern) for i in range(self.n_rules)))
 
 
 class DabModError(RuntimeError):
@@ -116,6 +136,22 @@ def lib():
     L.dabmod_b200_resampler_sizes.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.dabmod_b200_kernel_time.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, sz, ctypes.POINTER(ctypes.c_float)]
+    L.dabmod_b200_device_out.restype = vp
+    L.dabmod_b200_device_out.argtypes = [vp]
+    L.dabmod_b200_eti_describe.argtypes = [vp, sz, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(Stream), ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_int)]
+    L.dabmod_b200_coder_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Stream), ctypes.c_int,
+                                           ctypes.c_int, ctypes.POINTER(vp)]
+    L.dabmod_b200_coder_destroy.argtypes = [vp]
+    L.dabmod_b200_coder_tf_bytes.restype = sz
+    L.dabmod_b200_coder_tf_bytes.argtypes = [vp]
+    L.dabmod_b200_coder_frames_per_tf.argtypes = [vp]
+    L.dabmod_b200_coder_process.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
+    L.dabmod_b200_coder_process_device.argtypes = [vp, vp, sz, vp, vp]
+    L.dabmod_b200_coder_reset.argtypes = [vp]
+    L.dabmod_b200_coder_prime.argtypes = [vp, vp, sz]
+    L.dabmod_b200_process_eti_batch.argtypes = [vp, vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
+    L.dabmod_b200_coder_last_error.restype = ctypes.c_char_p
     _lib = L
     return L
 
@@ -300,6 +336,93 @@ class Modulator:
     def close(self):
         if getattr(self, "_h", None):
             lib().dabmod_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# Row N1: channel coding (ETI frames -> transmission-frame blocks)
+# ---------------------------------------------------------------------------
+ETI_FRAME = 6144
+
+
+def _check_coder(rc):
+    if rc != 0:
+        raise DabModError(rc, lib().dabmod_b200_coder_last_error().decode(errors="replace"))
+
+
+def make_streams(desc):
+    """[(framesize, out_bytes, start_cu, ((length, pattern), ...)), ...] -> dabmod_b200_stream array"""
+    arr = (Stream * len(desc))()
+    for i, d in enumerate(desc):
+        fs, ob, sc, rules = d.as_tuple() if isinstance(d, Stream) else d
+        arr[i].framesize, arr[i].out_bytes, arr[i].start_cu, arr[i].n_rules = fs, ob, sc, len(rules)
+        for k, (a, b) in enumerate(rules):
+            arr[i].rules[k] = Rule(a, b)
+    return arr
+
+
+def eti_describe(frame):
+    """(mode, [stream tuples]) from one ETI(NI) frame header: dabmod_b200_eti_describe (host only)."""
+    frame = np.ascontiguousarray(frame, np.uint8)
+    st = (Stream * 65)()
+    mode, n = ctypes.c_int(), ctypes.c_int()
+    _check_coder(lib().dabmod_b200_eti_describe(frame.ctypes.data, frame.size, ctypes.byref(mode), st, 65,
+                                                ctypes.byref(n)))
+    return mode.value, [st[i].as_tuple() for i in range(n.value)]
+
+
+class Coder:
+    """One multiplex configuration on one GPU (a dabmod_b200_coder handle)."""
+
+    def __init__(self, mode, streams, max_frames=4, device=0):
+        arr = make_streams(streams)
+        self._h = ctypes.c_void_p()
+        _check_coder(lib().dabmod_b200_coder_create(device, mode, arr, len(arr), max_frames, ctypes.byref(self._h)))
+        self.tf_bytes = lib().dabmod_b200_coder_tf_bytes(self._h)
+        self.frames_per_tf = lib().dabmod_b200_coder_frames_per_tf(self._h)
+        self.max_frames = max_frames
+
+    def process(self, frames):
+        """frames: (n, 6144) uint8, n a multiple of frames_per_tf -> (n / frames_per_tf, tf_bytes)"""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.size // ETI_FRAME
+        out = np.empty((n // max(self.frames_per_tf, 1)) * self.tf_bytes, np.uint8)
+        nb = ctypes.c_size_t()
+        _check_coder(lib().dabmod_b200_coder_process(self._h, frames.ctypes.data, n, out.ctypes.data, out.size,
+                                                     ctypes.byref(nb)))
+        return out[:nb.value].reshape(-1, self.tf_bytes)
+
+    def process_device(self, d_eti_ptr, n_frames, d_bits_ptr, stream=0):
+        _check_coder(lib().dabmod_b200_coder_process_device(self._h, d_eti_ptr, n_frames, d_bits_ptr, stream or None))
+
+    def prime(self, frames):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        _check_coder(lib().dabmod_b200_coder_prime(self._h, frames.ctypes.data, frames.size // ETI_FRAME))
+
+    def reset(self):
+        _check_coder(lib().dabmod_b200_coder_reset(self._h))
+
+    def modulate(self, modulator, frames):
+        """ETI frames -> I/Q through coder + modulator chained on the device."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.size // ETI_FRAME
+        n_tf = n // self.frames_per_tf
+        out = np.empty(n_tf * modulator.tf_out_bytes, np.uint8)
+        nb = ctypes.c_size_t()
+        _check_coder(lib().dabmod_b200_process_eti_batch(modulator._h, self._h, frames.ctypes.data, n,
+                                                         out.ctypes.data, out.size, ctypes.byref(nb)))
+        flat = out[:nb.value].view(modulator.out_dtype)
+        return flat.reshape(n_tf, flat.size // n_tf if n_tf else 0)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().dabmod_b200_coder_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -845,6 +845,8 @@ int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits
     });
 }
 
+void *dabmod_b200_device_out(dabmod_b200 *h) { return h ? (void *)h->d_out.p : nullptr; }
+
 uint64_t dabmod_b200_num_clipped_samples(dabmod_b200 *h) { return h ? h->clipped_last : 0; }
 uint32_t dabmod_b200_last_launch_count(const dabmod_b200 *h) { return h ? h->launches_last : 0; }
 

@@ -51,8 +51,8 @@ class Cfg(ctypes.Structure):
 
 def build():
     """Compile liboracle.so (gcc, ~1 s). Building the checker is not using it."""
-    src = os.path.join(HERE, "dabmod_oracle.c")
-    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("dabmod_oracle.c", "coder_oracle.c")]
+    if (not os.path.exists(LIB)) or any(os.path.getmtime(LIB) < os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     return LIB
 
@@ -199,6 +199,123 @@ class OracleChain:
     def close(self):
         if self._h:
             lib().dabo_chain_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------
+# Channel coding ahead of the path: coder_oracle.c
+# ---------------------------------------------------------------------------
+MAX_RULES = 8
+MAX_STREAMS = 65
+ETI_FRAME = 6144
+
+
+class Rule(ctypes.Structure):
+    _fields_ = [("length", ctypes.c_uint32), ("pattern", ctypes.c_uint32)]
+
+
+class Stream(ctypes.Structure):
+    _fields_ = [("framesize", ctypes.c_uint32), ("out_bytes", ctypes.c_uint32), ("start_cu", ctypes.c_uint32),
+                ("n_rules", ctypes.c_uint32), ("rules", Rule * MAX_RULES)]
+
+    def as_tuple(self):
+        return (self.framesize, self.out_bytes, self.start_cu,
+                tuple((self.rules[i].length, self.rules[i].pattern) for i in range(self.n_rules)))
+
+
+def _coder_lib():
+    L = lib()
+    if not getattr(L, "_coder_ready", False):
+        L.dabc_prbs.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        L.dabc_conv.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.dabc_puncture.restype = ctypes.c_long
+        L.dabc_puncture.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.POINTER(Rule), ctypes.c_int,
+                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_long]
+        L.dabc_describe.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(Stream), ctypes.c_int]
+        L.dabc_coder_new.restype = ctypes.c_void_p
+        L.dabc_coder_new.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(Stream)]
+        L.dabc_coder_free.argtypes = [ctypes.c_void_p]
+        L.dabc_coder_tf_bytes.argtypes = [ctypes.c_void_p]
+        L.dabc_coder_feed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L._coder_ready = True
+    return L
+
+
+def prbs(n):
+    out = np.zeros(n, np.uint8)
+    _coder_lib().dabc_prbs(n, out.ctypes.data)
+    return out
+
+
+def conv_encode(data):
+    data = np.ascontiguousarray(data, np.uint8)
+    out = np.zeros(4 * data.size + 3, np.uint8)
+    _coder_lib().dabc_conv(data.ctypes.data, data.size, out.ctypes.data)
+    return out
+
+
+def puncture(data, rules, out_bytes, tail=(3, 0xcccccc)):
+    data = np.ascontiguousarray(data, np.uint8)
+    r = (Rule * len(rules))(*[Rule(a, b) for a, b in rules])
+    out = np.zeros(out_bytes, np.uint8)
+    bits = _coder_lib().dabc_puncture(data.ctypes.data, data.size, r, len(rules), tail[0], tail[1],
+                                      out.ctypes.data, out_bytes)
+    return out, bits
+
+
+def describe_eti(frame):
+    """(mode, [Stream...]) from the header of one ETI(NI) frame; raises for UEP subchannels."""
+    frame = np.ascontiguousarray(frame, np.uint8)
+    st = (Stream * MAX_STREAMS)()
+    mode = ctypes.c_int()
+    n = _coder_lib().dabc_describe(frame.ctypes.data, ctypes.byref(mode), st, MAX_STREAMS)
+    if n < 0:
+        raise ValueError("dabc_describe: %d (%s)" % (n, "UEP tables are not derived by the oracle" if n == -2 else "bad frame"))
+    return mode.value, [st[i] for i in range(n)]
+
+
+def make_streams(desc):
+    """desc: [(framesize, out_bytes, start_cu, ((length, pattern), ...)), ...] -> Stream array"""
+    arr = (Stream * len(desc))()
+    for i, (fs, ob, sc, rules) in enumerate(desc):
+        arr[i].framesize, arr[i].out_bytes, arr[i].start_cu, arr[i].n_rules = fs, ob, sc, len(rules)
+        for k, (a, b) in enumerate(rules):
+            arr[i].rules[k] = Rule(a, b)
+    return arr
+
+
+class OracleCoder:
+    """ETI(NI) frames -> BlockPartitioner blocks, one multiplex configuration."""
+
+    def __init__(self, mode, streams):
+        if not isinstance(streams, ctypes.Array):
+            streams = make_streams([s.as_tuple() if isinstance(s, Stream) else s for s in streams])
+        self._streams = streams
+        self._h = _coder_lib().dabc_coder_new(mode, len(streams), streams)
+        if not self._h:
+            raise ValueError("dabc_coder_new rejected the configuration")
+        self.tf_bytes = _coder_lib().dabc_coder_tf_bytes(self._h)
+        self._out = np.zeros(self.tf_bytes, np.uint8)
+
+    def feed(self, frame):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        assert frame.size == ETI_FRAME
+        n = _coder_lib().dabc_coder_feed(self._h, frame.ctypes.data, self._out.ctypes.data)
+        return self._out.copy() if n else None
+
+    def run(self, frames):
+        out = [self.feed(f) for f in np.ascontiguousarray(frames, np.uint8).reshape(-1, ETI_FRAME)]
+        return [o for o in out if o is not None]
+
+    def close(self):
+        if self._h:
+            _coder_lib().dabc_coder_free(self._h)
             self._h = None
 
     def __del__(self):

@@ -148,3 +148,63 @@ class RefChain:
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------
+# Channel coding: the reference's EtiReader + coding graph,
+# oracle/ref_coder_harness.cpp
+# ---------------------------------------------------------------------------
+class RefCoder:
+    """Raw ETI(NI) frames in, BlockPartitioner blocks out, through the unmodified reference."""
+
+    def __init__(self):
+        L = lib()
+        L.refc_create.restype = ctypes.c_void_p
+        L.refc_destroy.argtypes = [ctypes.c_void_p]
+        L.refc_last_error.restype = ctypes.c_char_p
+        L.refc_feed.restype = ctypes.c_long
+        L.refc_feed.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.refc_describe.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int]
+        self._h = L.refc_create()
+        if not self._h:
+            raise RuntimeError(L.refc_last_error().decode())
+        self._out = np.zeros(4 * (384 + 6912), np.uint8)
+
+    def feed(self, frame):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        n = lib().refc_feed(self._h, frame.ctypes.data, frame.size, self._out.ctypes.data, self._out.size)
+        if n < 0:
+            raise RuntimeError(lib().refc_last_error().decode())
+        return self._out[:n].copy() if n else None
+
+    def run(self, frames):
+        out = [self.feed(f) for f in np.ascontiguousarray(frames, np.uint8).reshape(-1, 6144)]
+        return [o for o in out if o is not None]
+
+    def describe(self):
+        """[(framesize, out_bytes, start_cu, ((length, pattern), ...)), ...]: FIC first, as the
+        reference's FicSource / SubchannelSource objects report it (after the first frame)."""
+        cap_s, cap_r = 65, 512
+        fs, ob, st, nr = (np.zeros(cap_s, np.uint32) for _ in range(4))
+        rules = np.zeros(2 * cap_r, np.uint32)
+        n = lib().refc_describe(self._h, fs.ctypes.data, ob.ctypes.data, st.ctypes.data, nr.ctypes.data,
+                                rules.ctypes.data, cap_s, cap_r)
+        if n < 0:
+            raise RuntimeError(lib().refc_last_error().decode())
+        out, r = [], 0
+        for i in range(n):
+            rl = tuple((int(rules[2 * (r + k)]), int(rules[2 * (r + k) + 1])) for k in range(nr[i]))
+            r += int(nr[i])
+            out.append((int(fs[i]), int(ob[i]), int(st[i]), rl))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().refc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
