@@ -265,6 +265,59 @@ def measure_config(dm, torch, name, kw, n_tf, stream, peak, steps=5, warmup=3):
     return res
 
 
+def measure_coder(dm, torch, stream, n_tf=1024, steps=5, warmup=3, with_cpu=True):
+    """Row N1: ETI frames -> blocks (coder alone) and ETI frames -> I/Q (coder + TM I FIR chain),
+    device-resident, plus the reference's coding graph on one host core."""
+    import importlib
+    eti = importlib.import_module("odr_dabmod_b200.eti")
+    n_frames = n_tf * ETI_PER_TF
+    frames = eti.synth_eti(1, eti.default_multiplex(), n_frames, seed=11)
+    mode, streams = dm.eti_describe(frames[0])
+    cod = dm.Coder(mode, streams, max_frames=n_frames)
+    mod = dm.Modulator(mode=1, fir_taps="default", max_batch=n_tf)
+    d_eti = torch.from_numpy(frames).to("cuda")
+    d_bits = torch.empty(n_tf * cod.tf_bytes, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(n_tf * mod.tf_out_bytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def run(chain):
+        cod.process_device(d_eti.data_ptr(), n_frames, d_bits.data_ptr(), stream.cuda_stream)
+        if chain:
+            mod.process_batch_device(d_bits.data_ptr(), n_tf, d_out.data_ptr(), stream.cuda_stream)
+
+    res = {"workload": "n1 TM I, 6 x 128 kbit/s EEP 3-A + FIC: ETI(NI) frames in", "eti_frames_per_step": n_frames}
+    for key, chain in (("coder_only", False), ("eti_to_iq", True)):
+        for _ in range(warmup):
+            run(chain)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            run(chain)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[key] = {"ms_per_step": ms, "eti_frames_per_s": n_frames / (ms * 1e-3)}
+    # algorithmic traffic of the coder: ETI frame in, block out
+    res["coder_only"]["algorithmic_GB/s"] = n_frames * (6144 + 7200) / (res["coder_only"]["ms_per_step"] * 1e-3) / 1e9
+    if with_cpu:
+        try:
+            from oracle import refwrap
+            if refwrap.available():
+                ref = refwrap.RefCoder()
+                n_cpu = 2000
+                t0 = time.perf_counter()
+                ref.run(frames[:n_cpu])
+                dt = time.perf_counter() - t0
+                res["cpu_reference_coder"] = {"eti_frames_per_s": n_cpu / dt, "cores": 1, "kind": "reference",
+                                              "sample": "%d ETI frames through the reference's EtiReader + coding graph" % n_cpu}
+        except Exception as e:
+            res["cpu_reference_coder"] = {"error": str(e)}
+    cod.close()
+    mod.close()
+    return res
+
+
 def gpu_arm(args):
     import torch
     import dabmod_loader
@@ -294,6 +347,8 @@ def gpu_arm(args):
         for name, kw, ntf in other_configs():
             if name.startswith(args.only):
                 print(json.dumps(measure_config(dm, torch, name, kw, ntf, stream, peak, steps=args.steps)))
+        if args.only == "n1":
+            print(json.dumps(measure_coder(dm, torch, stream, steps=args.steps)))
         return 0
 
     n_tf = TFS_PER_STEP
@@ -408,6 +463,10 @@ def gpu_arm(args):
                 others.append(measure_config(dm, torch, name, kw, ntf, stream, peak))
             except Exception as e:                       # an extra must never cost the headline line
                 others.append({"workload": name, "error": str(e)})
+        try:
+            others.append(measure_coder(dm, torch, stream, with_cpu=not args.no_cpu))
+        except Exception as e:
+            others.append({"workload": "n1 coder", "error": str(e)})
 
     line = {
         "metric": METRIC, "value": value, "unit": "ETI frames/s", "n_gpus": world,

@@ -42,73 +42,119 @@ struct CoderError : std::runtime_error {
             throw CoderError(DABMOD_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+constexpr int MAX_SEGMENTS = 16;
+constexpr int CODE_THREADS = 128;
+
+// One application of a puncturing rule: `n_groups` groups of 4 encoder bytes (= 8 input bits)
+// starting at group `first_group`, each keeping the `kept` bits selected by `mask`.
+struct Segment {
+    int first_group, n_groups;
+    uint32_t mask;
+    int kept;          // popcount(mask)
+    int out_bit;       // output bit offset of the segment's first kept bit
+};
+
 // per stream, device side
 struct StreamDev {
     int in_off;        // byte offset of the stream's data inside an ETI frame
-    int framesize;     // input bytes
+    int framesize;     // input bytes = number of full groups
     int out_bytes;     // punctured bytes per frame
     int punct_off;     // byte offset inside a punctured row
-    int map_off;       // offset (in entries) into the bit map
     int start_byte;    // start address * 8 inside the CIF (subchannels)
-    int words;         // out_bytes / 4
-    int word0;         // first work item (output word) of this stream within a frame
+    int n_segments;
+    int tail_out_bit;  // output bit offset of the tail rule (3, 0xcccccc)
+    Segment seg[MAX_SEGMENTS];
 };
 
 struct CodeParams {
     const uint8_t *eti;          // n_frames * 6144
     const StreamDev *streams;
-    const uint32_t *map;         // per output bit: (input bit i << 2) | generator, 0xffffffff = padding
     const uint8_t *prbs;         // 6912 bytes
     uint8_t *punct;              // ring of rows, row_bytes each
-    int n_streams, words_per_frame, row_bytes, ring_rows, ring_base, n_frames;
+    int n_streams, row_bytes, ring_rows, ring_base, n_frames;
 };
 
-// PrbsGenerator.cpp:126-188, ConvEncoder.cpp:59-150, PuncturingEncoder.cpp:102-210.
-// One warp = one 32-bit output word of one (frame, stream): lane l computes output bit l.
-__global__ void __launch_bounds__(256) k_code(const __grid_constant__ CodeParams p)
+// bit t of the byte c -> bit 4t of the result
+__device__ __forceinline__ uint32_t spread_byte(uint32_t c)
 {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long total = (long long)p.n_frames * p.words_per_frame;
-    if (warp >= total) return;
-    const int frame = (int)(warp / p.words_per_frame);
-    const int item = (int)(warp - (long long)frame * p.words_per_frame);
-    // stream of this work item (streams are few: linear search, uniform across the warp)
-    int s = 0;
-    while (s + 1 < p.n_streams && item >= p.streams[s + 1].word0) s++;
-    const StreamDev st = p.streams[s];
-    const int w = item - st.word0;
-    const uint8_t *in = p.eti + (size_t)frame * ETI_FRAME + st.in_off;
+    c = (c | (c << 12)) & 0x000f000fu;
+    c = (c | (c << 6)) & 0x03030303u;
+    c = (c | (c << 3)) & 0x11111111u;
+    return c;
+}
 
-    const uint32_t m = __ldg(p.map + st.map_off + 32 * w + lane);
-    unsigned bit = 0;
-    if (m != 0xffffffffu) {
-        const int i = (int)(m >> 2);                    // newest input bit of the encoder register
-        const int g = (int)(m & 3u);
-        // scrambled input bits i-6 .. i, MSB first; bits before the frame and the 6 tail bits are 0
-        unsigned win = 0;
-        const int lo = i - 6;
-        const int q0 = lo >> 3;                          // may be -1 (arithmetic shift)
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int q = q0 + k;
-            unsigned b = 0;
-            if (q >= 0 && q < st.framesize) b = (unsigned)__ldg(in + q) ^ (unsigned)__ldg(p.prbs + q);
-            win = (win << 8) | b;
+// The 32 encoder output bits of the 8 input bits in the low byte of `w` (bits 13..8 of `w` = the six
+// input bits before them): ConvEncoder.cpp:88-108.  Generators 0x5b 0x79 0x65 0x5b act on a register
+// that holds the newest bit at bit 6, i.e. on input ages {0,2,3,5,6}, {0,1,2,3,6}, {0,1,4,6}.
+// Result: first input bit in the top nibble, generator 0 in the nibble's MSB.
+__device__ __forceinline__ uint32_t conv8(uint32_t w)
+{
+    const uint32_t c0 = (w ^ (w >> 2) ^ (w >> 3) ^ (w >> 5) ^ (w >> 6)) & 0xffu;
+    const uint32_t c1 = (w ^ (w >> 1) ^ (w >> 2) ^ (w >> 3) ^ (w >> 6)) & 0xffu;
+    const uint32_t c2 = (w ^ (w >> 1) ^ (w >> 4) ^ (w >> 6)) & 0xffu;
+    const uint32_t s0 = spread_byte(c0);
+    return (s0 << 3) | (spread_byte(c1) << 2) | (spread_byte(c2) << 1) | s0;
+}
+
+// the bits of `v` selected by `mask`, packed MSB first (PuncturingEncoder.cpp:152-166)
+__device__ __forceinline__ uint32_t extract_bits(uint32_t v, uint32_t mask)
+{
+    uint32_t out = 0;
+    while (mask) {
+        const int b = 31 - __clz(mask);
+        out = (out << 1) | ((v >> b) & 1u);
+        mask &= ~(1u << b);
+    }
+    return out;
+}
+
+// ORs the `n` low bits of `v` into the big-endian bit string `buf` at bit offset `o`
+__device__ __forceinline__ void put_bits(uint32_t *buf, int o, uint32_t v, int n, int cap_bits)
+{
+    if (n == 0 || o >= cap_bits) return;
+    const int j = o >> 5, r = o & 31;
+    if (r + n <= 32) {
+        atomicOr(buf + j, v << (32 - r - n));
+    }
+    else {
+        atomicOr(buf + j, v >> (r + n - 32));
+        if (((j + 1) << 5) < cap_bits) atomicOr(buf + j + 1, v << (64 - r - n));
+    }
+}
+
+// PrbsGenerator.cpp:126-188, ConvEncoder.cpp:59-150, PuncturingEncoder.cpp:102-210.
+// One CTA = one (frame, stream); one thread = one group of 8 input bits: 32 encoder bits by
+// shift-and-XOR, the kept ones packed and OR-ed into the row at the position the rule table gives.
+__global__ void __launch_bounds__(CODE_THREADS) k_code(const __grid_constant__ CodeParams p)
+{
+    __shared__ uint32_t row[CIF_BYTES / 4];
+    __shared__ uint8_t scr[ETI_FRAME];
+    const int frame = blockIdx.x / p.n_streams, s = blockIdx.x - frame * p.n_streams;
+    const StreamDev &st = p.streams[s];
+    const int n = st.framesize, words = st.out_bytes / 4, cap_bits = st.out_bytes * 8;
+    const uint8_t *in = p.eti + (size_t)frame * ETI_FRAME + st.in_off;
+    for (int i = threadIdx.x; i < n; i += CODE_THREADS) scr[i] = __ldg(in + i) ^ __ldg(p.prbs + i);
+    for (int i = threadIdx.x; i < words; i += CODE_THREADS) row[i] = 0;
+    __syncthreads();
+    for (int g = threadIdx.x; g <= n; g += CODE_THREADS) {
+        const uint32_t prev = g > 0 ? scr[g - 1] : 0u;
+        if (g < n) {
+            const uint32_t c = conv8((prev << 8) | scr[g]);
+            int k = 0;
+            while (k + 1 < st.n_segments && g >= st.seg[k + 1].first_group) k++;
+            const Segment sg = st.seg[k];
+            put_bits(row, sg.out_bit + (g - sg.first_group) * sg.kept, extract_bits(c, sg.mask), sg.kept, cap_bits);
         }
-        const int sh = 9 - (lo & 7);                     // window = bits [lo, lo+6] of the 16-bit pair
-        win = (win >> sh) & 0x7fu;
-        // generators 0x5b 0x79 0x65 0x5b act on a register holding the newest bit at bit 6;
-        // `win` holds it at bit 0, so the masks are bit-reversed
-        const unsigned rpoly = g == 1 ? 0x4fu : g == 2 ? 0x53u : 0x6du;
-        bit = __popc(win & rpoly) & 1u;
+        else {
+            // six zero tail bits -> 24 encoder bits, tail rule 0xcccccc keeps 12
+            const uint32_t c = conv8(prev << 8) >> 8;
+            put_bits(row, st.tail_out_bit, extract_bits(c, 0xccccccu), 12, cap_bits);
+        }
     }
-    const unsigned word = __brev(__ballot_sync(0xffffffffu, bit));   // lane 0 = MSB of byte 0
-    if (lane == 0) {
-        const int row = (p.ring_base + (TI_DEPTH - 1) + frame) % p.ring_rows;
-        uint32_t *dst = reinterpret_cast<uint32_t *>(p.punct + (size_t)row * p.row_bytes + st.punct_off) + w;
-        *dst = __byte_perm(word, 0, 0x0123);
-    }
+    __syncthreads();
+    const int r = (p.ring_base + (TI_DEPTH - 1) + frame) % p.ring_rows;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(p.punct + (size_t)r * p.row_bytes + st.punct_off);
+    for (int i = threadIdx.x; i < words; i += CODE_THREADS) dst[i] = __byte_perm(row[i], 0, 0x0123);
 }
 
 struct MuxParams {
@@ -118,47 +164,48 @@ struct MuxParams {
     const uint8_t *prbs;
     uint8_t *bits;               // n_tf * tf_bytes
     int row_bytes, ring_rows, ring_base, cif_count, fic_out, tf_bytes;
-    long long total;             // n_tf * tf_bytes
+    long long total_words;       // n_tf * tf_bytes / 4
 };
 
 // TimeInterleaver.cpp:51-96, FrameMultiplexer.cpp:43-91, BlockPartitioner.cpp:78-124.
-// One thread = one byte of the transmission-frame block.
+// One thread = four bytes of the transmission-frame block (all sizes and offsets are multiples of 8).
 __global__ void __launch_bounds__(256) k_mux(const __grid_constant__ MuxParams p)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.total) return;
-    const int tf = (int)(idx / p.tf_bytes);
-    const int o = (int)(idx - (long long)tf * p.tf_bytes);
+    if (idx >= p.total_words) return;
+    const int wpt = p.tf_bytes / 4;
+    const int tf = (int)(idx / wpt);
+    const int o = (int)(idx - (long long)tf * wpt) * 4;
     const int fic_total = p.cif_count * p.fic_out;
-    uint8_t v;
+    uint32_t v;
     if (o < fic_total) {
         const int part = o / p.fic_out, j = o - part * p.fic_out;
         const int row = (p.ring_base + (TI_DEPTH - 1) + tf * p.cif_count + part) % p.ring_rows;
-        v = p.punct[(size_t)row * p.row_bytes + j];                 // the FIC is stream 0 at offset 0
+        v = *reinterpret_cast<const uint32_t *>(p.punct + (size_t)row * p.row_bytes + j);   // FIC = stream 0 at offset 0
     }
     else {
         const int c = (o - fic_total) / CIF_BYTES, b = (o - fic_total) - c * CIF_BYTES;
         const int s = p.owner[b >> 3];
         if (s == 0) {
-            v = p.prbs[b];
+            v = *reinterpret_cast<const uint32_t *>(p.prbs + b);
         }
         else {
-            const StreamDev st = p.streams[s];
-            const int j = b - st.start_byte;
+            const StreamDev &st = p.streams[s];
+            const int j = b - st.start_byte;             // multiple of 4: bytes j, j+2 even, j+1, j+3 odd
             const int newest = p.ring_base + (TI_DEPTH - 1) + tf * p.cif_count + c;
-            // bit 7..0 of byte j come from the frames 0,8,4,12,2,10,6,14 (+1 for odd j) calls back
-            const int odd = j & 1;
-            unsigned acc = 0;
+            // bit 7..0 of a byte come from the frames 0,8,4,12,2,10,6,14 (+1 for odd bytes) calls back
+            v = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const int d = ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | odd;
-                const int row = (newest - d) % p.ring_rows;
-                acc |= p.punct[(size_t)row * p.row_bytes + st.punct_off + j] & (0x80u >> k);
+                const int d = ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1);
+                const int r0 = (newest - d) % p.ring_rows, r1 = (newest - d - 1) % p.ring_rows;
+                const uint32_t e = *reinterpret_cast<const uint32_t *>(p.punct + (size_t)r0 * p.row_bytes + st.punct_off + j);
+                const uint32_t q = *reinterpret_cast<const uint32_t *>(p.punct + (size_t)r1 * p.row_bytes + st.punct_off + j);
+                v |= (e & (0x00800080u >> k)) | (q & (0x80008000u >> k));
             }
-            v = (uint8_t)acc;
         }
     }
-    p.bits[idx] = v;
+    reinterpret_cast<uint32_t *>(p.bits)[idx] = v;
 }
 
 thread_local std::string g_coder_error;
@@ -196,12 +243,11 @@ const uint32_t PI_MASK[25] = {0,
 
 struct dabmod_b200_coder {
     int device = 0, mode = 1, cif_count = 4, fic_out = 288, tf_bytes = 28800;
-    int n_streams = 0, max_frames = 0, row_bytes = 0, ring_rows = 0, ring_base = 0, words_per_frame = 0;
+    int n_streams = 0, max_frames = 0, row_bytes = 0, ring_rows = 0, ring_base = 0;
     std::vector<StreamDev> streams;
     std::mutex mtx;
     cudaStream_t stream = nullptr;
     StreamDev *d_streams = nullptr;
-    uint32_t *d_map = nullptr;
     uint8_t *d_prbs = nullptr, *d_owner = nullptr, *d_punct = nullptr, *d_eti = nullptr, *d_bits = nullptr;
 };
 
@@ -267,7 +313,7 @@ void dabmod_b200_coder_destroy(dabmod_b200_coder *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    cudaFree(c->d_streams); cudaFree(c->d_map); cudaFree(c->d_prbs); cudaFree(c->d_owner);
+    cudaFree(c->d_streams); cudaFree(c->d_prbs); cudaFree(c->d_owner);
     cudaFree(c->d_punct); cudaFree(c->d_eti); cudaFree(c->d_bits);
     delete c;
 }
@@ -295,66 +341,58 @@ int dabmod_b200_coder_create(int device, int mode, const dabmod_b200_stream *st,
         c->n_streams = n_streams;
         c->max_frames = std::max(max_frames, c->cif_count);
 
-        std::vector<uint32_t> map;
         std::vector<uint8_t> owner(864, 0);
-        int in_off = 8 + 4 * (n_streams - 1) + 4, punct_off = 0, word0 = 0;
+        int in_off = 8 + 4 * (n_streams - 1) + 4, punct_off = 0;
         for (int s = 0; s < n_streams; s++) {
             const dabmod_b200_stream &d = st[s];
             if (d.n_rules < 1 || d.n_rules > 8) throw CoderError(DABMOD_B200_EINVAL, "stream needs 1..8 puncturing rules");
-            if (d.framesize == 0 || d.out_bytes == 0 || (d.out_bytes & 3))
+            if (d.framesize == 0 || d.out_bytes == 0 || (d.out_bytes & 7) || d.out_bytes > (uint32_t)CIF_BYTES)
                 throw CoderError(DABMOD_B200_EINVAL, "invalid stream size");
             if (in_off + (int)d.framesize + 8 > ETI_FRAME) throw CoderError(DABMOD_B200_EINVAL, "streams exceed the ETI frame");
             if (s == 0 && (int)d.out_bytes != c->fic_out)
                 throw CoderError(DABMOD_B200_EINVAL, "BlockPartitioner::process input 0 size not valid!");
             if (s > 0 && d.start_cu * 8 + d.out_bytes > (uint32_t)CIF_BYTES)
                 throw CoderError(DABMOD_B200_EINVAL, "subchannel exceeds the CIF");
-            // Expand the puncturing rules (PuncturingEncoder.cpp:148-196) into one source index per
-            // output bit: the index of the kept convolutional-encoder bit, 4 * input bit + generator.
-            const long body = 4L * d.framesize;                  // encoder bytes before the 3 tail bytes
-            const size_t base = map.size();
-            const long cap_bits = (long)d.out_bytes * 8;
-            map.resize(base + (size_t)cap_bits, 0xffffffffu);
-            long ob = 0, ic = 0;
+            // The puncturing rules (PuncturingEncoder.cpp:148-196) as a table of segments: rules are
+            // consumed in order and cycled, each covers length/4 groups of 4 encoder bytes.
+            StreamDev sd{};
+            const long groups = d.framesize;                     // 4 encoder bytes per input byte
+            long g = 0, ob = 0;
             uint32_t r = 0;
-            while (ic < body) {
+            while (g < groups) {
                 if (d.rules[r].length == 0 || (d.rules[r].length & 3))
                     throw CoderError(DABMOD_B200_EINVAL, "puncturing rule length must be a positive multiple of 4");
-                for (long len = d.rules[r].length; len > 0 && ic < body; len -= 4, ic += 4)
-                    for (int k = 0; k < 32; k++)
-                        if (d.rules[r].pattern & (0x80000000u >> k)) {
-                            if (ob < cap_bits) map[base + ob] = (uint32_t)(ic * 8 + k);
-                            ob++;
-                        }
+                if (sd.n_segments == MAX_SEGMENTS)
+                    throw CoderError(DABMOD_B200_EUNSUPPORTED, "more than 16 puncturing rule applications per frame");
+                Segment &sg = sd.seg[sd.n_segments++];
+                sg.first_group = (int)g;
+                sg.n_groups = (int)std::min<long>(d.rules[r].length / 4, groups - g);
+                sg.mask = d.rules[r].pattern;
+                sg.kept = __builtin_popcount(sg.mask);
+                sg.out_bit = (int)ob;
+                g += sg.n_groups;
+                ob += (long)sg.n_groups * sg.kept;
                 if (++r == d.n_rules) r = 0;
             }
-            for (int k = 0; k < 24; k++)                          // tail rule (3, 0xcccccc), DabModulator.cpp:316,373
-                if (0xccccccu & (0x800000u >> k)) {
-                    if (ob < cap_bits) map[base + ob] = (uint32_t)(ic * 8 + k);
-                    ob++;
-                }
+            sd.tail_out_bit = (int)ob;
+            ob += 12;                                            // tail rule (3, 0xcccccc), DabModulator.cpp:316,373
             // PuncturingEncoder.cpp:120-134: the kept bits must fill the block (UEP: one byte of padding allowed)
             const long need = (ob + 7) / 8;
             if (!(need == (long)d.out_bytes || (s > 0 && need + 1 == (long)d.out_bytes)))
                 throw CoderError(DABMOD_B200_EINVAL, "PuncturingEncoder encoder initialisation failed. block_size: " +
                                                          std::to_string(need) + " out_bytes: " + std::to_string(d.out_bytes));
-            StreamDev sd{};
             sd.in_off = in_off;
             sd.framesize = (int)d.framesize;
             sd.out_bytes = (int)d.out_bytes;
             sd.punct_off = punct_off;
-            sd.map_off = (int)base;
             sd.start_byte = (int)d.start_cu * 8;
-            sd.words = (int)d.out_bytes / 4;
-            sd.word0 = word0;
             c->streams.push_back(sd);
             if (s > 0)
                 for (uint32_t cu = d.start_cu; cu < d.start_cu + d.out_bytes / 8; cu++) owner[cu] = (uint8_t)s;
             in_off += (int)d.framesize;
             punct_off += (int)d.out_bytes;
-            word0 += sd.words;
         }
         c->row_bytes = punct_off;
-        c->words_per_frame = word0;
         c->ring_rows = (TI_DEPTH - 1) + c->max_frames;
         c->ring_base = 0;
 
@@ -373,14 +411,12 @@ int dabmod_b200_coder_create(int device, int mode, const dabmod_b200_stream *st,
 
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaMalloc((void **)&c->d_streams, sizeof(StreamDev) * c->streams.size()));
-        CK(cudaMalloc((void **)&c->d_map, sizeof(uint32_t) * map.size()));
         CK(cudaMalloc((void **)&c->d_prbs, prbs.size()));
         CK(cudaMalloc((void **)&c->d_owner, owner.size()));
         CK(cudaMalloc((void **)&c->d_punct, (size_t)c->ring_rows * c->row_bytes));
         CK(cudaMalloc((void **)&c->d_eti, (size_t)c->max_frames * ETI_FRAME));
         CK(cudaMalloc((void **)&c->d_bits, (size_t)(c->max_frames / c->cif_count) * c->tf_bytes));
         CK(cudaMemcpy(c->d_streams, c->streams.data(), sizeof(StreamDev) * c->streams.size(), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(c->d_map, map.data(), sizeof(uint32_t) * map.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_prbs, prbs.data(), prbs.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_owner, owner.data(), owner.size(), cudaMemcpyHostToDevice));
         CK(cudaMemset(c->d_punct, 0, (size_t)c->ring_rows * c->row_bytes));
@@ -400,17 +436,14 @@ static void coder_enqueue(dabmod_b200_coder *c, const uint8_t *d_eti, size_t n_f
     CodeParams cp{};
     cp.eti = d_eti;
     cp.streams = c->d_streams;
-    cp.map = c->d_map;
     cp.prbs = c->d_prbs;
     cp.punct = c->d_punct;
     cp.n_streams = c->n_streams;
-    cp.words_per_frame = c->words_per_frame;
     cp.row_bytes = c->row_bytes;
     cp.ring_rows = c->ring_rows;
     cp.ring_base = c->ring_base;
     cp.n_frames = (int)n_frames;
-    const long long warps = (long long)n_frames * c->words_per_frame;
-    k_code<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(cp);
+    k_code<<<(unsigned)(n_frames * c->n_streams), CODE_THREADS, 0, s>>>(cp);
     CK(cudaGetLastError());
     if (d_bits) {
         MuxParams mp{};
@@ -425,8 +458,8 @@ static void coder_enqueue(dabmod_b200_coder *c, const uint8_t *d_eti, size_t n_f
         mp.cif_count = c->cif_count;
         mp.fic_out = c->fic_out;
         mp.tf_bytes = c->tf_bytes;
-        mp.total = (long long)(n_frames / c->cif_count) * c->tf_bytes;
-        k_mux<<<(unsigned)((mp.total + 255) / 256), 256, 0, s>>>(mp);
+        mp.total_words = (long long)(n_frames / c->cif_count) * c->tf_bytes / 4;
+        k_mux<<<(unsigned)((mp.total_words + 255) / 256), 256, 0, s>>>(mp);
         CK(cudaGetLastError());
     }
     c->ring_base = (int)((c->ring_base + n_frames) % c->ring_rows);
