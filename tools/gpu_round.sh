@@ -1,17 +1,17 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full capture of the kernels.
+# One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list + full captures of the kernels.
 # usage: bash tools/gpu_round.sh [tag]   (NCU=0 skips the profiler passes)
 set -x
 TAG=${1:-cur}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-./tools/ubench/fp32_pipes > gpurun_out/fp32_pipes.txt 2>&1; cat gpurun_out/fp32_pipes.txt
-python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+python -m pytest tests -x -q -m gpu 2>&1 | tail -5
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench.err
+python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref_$TAG.json
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench.err; tail -c 6000 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench.err
 if [ "${NCU:-1}" = "1" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_symbols -s 2 -c 1 -f -o gpurun_out/prof_symbols_$TAG python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_sym.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_fir -s 2 -c 1 -f -o gpurun_out/prof_fir_$TAG python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_fir.log 2>&1
-ls -la gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/ncu_bench.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_symbols -s 2 -c 1 -f -o gpurun_out/prof_symbols_$TAG python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/ncu_sym.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_fir -s 2 -c 1 -f -o gpurun_out/prof_fir_$TAG python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/ncu_fir.log 2>&1
+ls -la gpurun_out | tail -8
 fi
