@@ -161,6 +161,13 @@ def _check(rc):
         raise DabModError(rc, lib().dabmod_b200_last_error().decode(errors="replace"))
 
 
+def resampler_sizes(in_rate, out_rate, resolution):
+    """(Ni, No) the reference's Resampler picks for this ratio (Resampler.cpp:65-76)."""
+    ni, no = ctypes.c_int(), ctypes.c_int()
+    _check(lib().dabmod_b200_resampler_sizes(in_rate, out_rate, resolution, ctypes.byref(ni), ctypes.byref(no)))
+    return ni.value, no.value
+
+
 def default_fir_taps():
     n = lib().dabmod_b200_default_fir_taps(None, 0)
     t = np.zeros(n, np.float32)

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "resample.cuh"
 #include "resample_up.cuh"
+#include "resample_q.cuh"
 #include "symbols_warp.cuh"
 #include "tables.h"
 
@@ -130,6 +131,7 @@ struct dabmod_b200 {
     DevBuf<float2> d_scratch;
     int res_grid = 0;
     bool res_up = false;           // k_resample_up applies (Ni = 4096, integer ratio <= 4)
+    bool res_q = false;            // k_resample_q applies (Ni = 4096, No = P * 4000, P = 2..5)
     bool allow_res_up = true;      // "res_kernel" knob: 0 = always the generic kernel
     size_t res_smem = 0;
 
@@ -456,6 +458,27 @@ void enqueue_resampler(dabmod_b200 *h, const float2 *in, size_t n_tf, void *d_ou
         prof.end();
         launches++;
     }
+    else if (h->res_q && h->allow_res_up) {
+        // TM I, No = P * 4000 (4 / 6 / 8 / 10 Msps): P phase transforms of 4000 points per hop in shared memory
+        RqParams pq{};
+        pq.r = p;
+        pq.P = rp.no / RQ_Q;
+        const int grid = (int)std::min<long long>((p.total_hops + RQ_TEAMS - 1) / RQ_TEAMS, h->sm_count);
+        ProfScope prof(h, "k_resample_q", s);
+        if (post) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_resample_q<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(RqSmem)));
+            k_resample_q<true><<<grid, RQ_THREADS, sizeof(RqSmem), s>>>(pq);
+        }
+        else {
+            CUDA_CHECK(cudaFuncSetAttribute(k_resample_q<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(RqSmem)));
+            k_resample_q<false><<<grid, RQ_THREADS, sizeof(RqSmem), s>>>(pq);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        prof.end();
+        launches++;
+    }
     else {
     const int grid = (int)std::min<long long>(p.total_hops, h->res_grid);
     ProfScope prof(h, "k_resample", s);
@@ -641,6 +664,8 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
             h->rp = rp;
             h->has_res = true;
             h->res_up = rp.ni == RU_NI && rp.M == 1 && rp.L >= 2 && rp.L <= (uint64_t)RU_MAX_L;
+            h->res_q = rp.ni == RQ_NI && rp.no > rp.ni && rp.no % RQ_Q == 0 && rp.no / RQ_Q >= RQ_MIN_P &&
+                       rp.no / RQ_Q <= RQ_MAX_P;
             h->d_res_win.upload(resampler_window(rp.ni), h->s_compute);
             std::vector<float> t;
             twiddle_table(rp.ni, t);

@@ -24,10 +24,12 @@ namespace dabmod {
 DABMOD_FN float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 DABMOD_FN float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 DABMOD_FN float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+DABMOD_FN float2 cfma(float s, float2 a, float2 c) { return __ffma2_rn(make_float2(s, s), a, c); }
 #else
 DABMOD_FN float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 DABMOD_FN float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 DABMOD_FN float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+DABMOD_FN float2 cfma(float s, float2 a, float2 c) { return make_float2(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y)); }
 #endif
 DABMOD_FN float2 cmul(float2 a, float2 b)
 {
@@ -142,6 +144,60 @@ DABMOD_FN void fft16(float2 *v)
             v[4 * k + m] = v[4 * m + k];
             v[4 * m + k] = t;
         }
+}
+
+// ---- radix 5 / 10 / 20 (the 4000-point phase transforms of k_resample_q) ----
+// 5-point DFT in place: X[k] = sum_n x[n] e^{+-j 2 pi n k / 5}
+template <bool INV>
+DABMOD_FN void dft5(float2 &x0, float2 &x1, float2 &x2, float2 &x3, float2 &x4)
+{
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos 72, cos 144
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin 72, sin 144
+    const float2 t1 = cadd(x1, x4), t2 = cadd(x2, x3), t3 = csub(x1, x4), t4 = csub(x2, x3);
+    const float2 a = cfma(c1, t1, cfma(c2, t2, x0));
+    const float2 b = cfma(c2, t1, cfma(c1, t2, x0));
+    const float2 p = cfma(s1, t3, cscale(t4, s2));
+    const float2 q = cfma(s2, t3, cscale(t4, -s1));
+    x0 = cadd(x0, cadd(t1, t2));
+    x1 = cadd_j<INV>(a, p);
+    x4 = csub_j<INV>(a, p);
+    x2 = cadd_j<INV>(b, q);
+    x3 = csub_j<INV>(b, q);
+}
+
+// 20 = 4 x 5 with coprime factors: the prime-factor index maps n = (5 n1 + 4 n2) mod 20,
+// k = (5 k1 + 16 k2) mod 20 need no twiddles between the two stages, and every index below is a
+// compile-time register number.  v[0..19] natural order in, natural order out.
+template <bool INV>
+DABMOD_FN void fft20(float2 *v)
+{
+#pragma unroll
+    for (int n1 = 0; n1 < 4; n1++)
+        dft5<INV>(v[(5 * n1) % 20], v[(5 * n1 + 4) % 20], v[(5 * n1 + 8) % 20], v[(5 * n1 + 12) % 20],
+                  v[(5 * n1 + 16) % 20]);
+#pragma unroll
+    for (int k2 = 0; k2 < 5; k2++)
+        fft4<INV>(v[(4 * k2) % 20], v[(5 + 4 * k2) % 20], v[(10 + 4 * k2) % 20], v[(15 + 4 * k2) % 20]);
+    float2 o[20];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++)
+#pragma unroll
+        for (int k2 = 0; k2 < 5; k2++) o[(5 * k1 + 16 * k2) % 20] = v[(5 * k1 + 4 * k2) % 20];
+#pragma unroll
+    for (int i = 0; i < 20; i++) v[i] = o[i];
+}
+
+// 10 = 2 x 5 the same way (n = (5 n1 + 2 n2) mod 10, k = (5 k1 + 6 k2) mod 10), but only the
+// first five outputs: X[k] = Y0[k] + (-1)^k Y1[k], k < 5.  v[0..9] in, v[0..4] out.
+template <bool INV>
+DABMOD_FN void fft10_lo(float2 *v)
+{
+    dft5<INV>(v[0], v[2], v[4], v[6], v[8]);
+    dft5<INV>(v[5], v[7], v[9], v[1], v[3]);
+    // Y0[k2] sits at v[2 k2], Y1[k2] at v[(5 + 2 k2) % 10]
+    const float2 o0 = cadd(v[0], v[5]), o1 = csub(v[2], v[7]), o2 = cadd(v[4], v[9]);
+    const float2 o3 = csub(v[6], v[1]), o4 = cadd(v[8], v[3]);
+    v[0] = o0; v[1] = o1; v[2] = o2; v[3] = o3; v[4] = o4;
 }
 
 template <int R, bool INV>

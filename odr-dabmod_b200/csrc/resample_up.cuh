@@ -67,7 +67,8 @@ __device__ __forceinline__ void ru_powers(const float2 *tab, int Ns, int k, floa
 // 4096-point transform of the 16 values of butterfly t (element t + 256 r in v[r]), in place
 // through the team's buffer; on return v[r] = X[t + 256 r].
 template <bool INV>
-__device__ __forceinline__ void ru_fft4096(float2 (&v)[16], float2 *buf, const RuSmem &sm, int t, int team)
+__device__ __forceinline__ void ru_fft4096(float2 (&v)[16], float2 *buf, const float2 *tw2, const float2 *tw3, int t,
+                                           int team)
 {
     // pass 1 (Ns = 1): no twiddles, out[t*16 + r]
     fft16<INV>(v);
@@ -81,7 +82,7 @@ __device__ __forceinline__ void ru_fft4096(float2 (&v)[16], float2 *buf, const R
 #pragma unroll
         for (int r = 0; r < 16; r++) v[r] = buf[spad(t + 256 * r)];
         float2 w[16];
-        ru_powers(sm.tw2, 16, k, w);
+        ru_powers(tw2, 16, k, w);
 #pragma unroll
         for (int r = 1; r < 16; r++) v[r] = cmul(v[r], tw_dir<INV>(w[r]));
         fft16<INV>(v);
@@ -96,7 +97,7 @@ __device__ __forceinline__ void ru_fft4096(float2 (&v)[16], float2 *buf, const R
 #pragma unroll
         for (int r = 0; r < 16; r++) v[r] = buf[spad(t + 256 * r)];
         float2 w[16];
-        ru_powers(sm.tw3, 256, t, w);
+        ru_powers(tw3, 256, t, w);
 #pragma unroll
         for (int r = 1; r < 16; r++) v[r] = cmul(v[r], tw_dir<INV>(w[r]));
         fft16<INV>(v);
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
                 c_lo[r] = v[r];
             }
         }
-        ru_fft4096<false>(v, buf, sm, t, team);
+        ru_fft4096<false>(v, buf, sm.tw2, sm.tw3, t, team);
         // v[r] = F[t + 256 r].  Keep it; publish the Nyquist bin (t = 0, r = 8).
         float2 F[16];
 #pragma unroll
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
                 if (k == hi) w = make_float2(w.x + w.x, 0.f);   // e^{+j a} + e^{-j a} = 2 cos a
                 v[r] = cmul(F[r], w);
             }
-            ru_fft4096<true>(v, buf, sm, t, team);
+            ru_fft4096<true>(v, buf, sm.tw2, sm.tw3, t, team);
 #pragma unroll
             for (int r = 0; r < 8; r++)
                 sm.stage[team][rho][t + 256 * r] = make_float2(v[r].x * p.factor, v[r].y * p.factor);

@@ -43,6 +43,27 @@ extern "C" int fft_host(int n, int inv, float *io)
             for (int i = 0; i < 64; i++) v[i] = a[i];
             return 0;
         }
+        case 5: {
+            float2 a[5];
+            for (int i = 0; i < 5; i++) a[i] = v[i];
+            if (inv) dft5<true>(a[0], a[1], a[2], a[3], a[4]); else dft5<false>(a[0], a[1], a[2], a[3], a[4]);
+            for (int i = 0; i < 5; i++) v[i] = a[i];
+            return 0;
+        }
+        case 20: {
+            float2 a[20];
+            for (int i = 0; i < 20; i++) a[i] = v[i];
+            if (inv) fft20<true>(a); else fft20<false>(a);
+            for (int i = 0; i < 20; i++) v[i] = a[i];
+            return 0;
+        }
+        case -10: {  // fft10_lo: the first five outputs of a 10-point transform
+            float2 a[10];
+            for (int i = 0; i < 10; i++) a[i] = v[i];
+            if (inv) fft10_lo<true>(a); else fft10_lo<false>(a);
+            for (int i = 0; i < 5; i++) v[i] = a[i];
+            return 0;
+        }
         case -8: {   // fft8r, the by-reference variant
             float2 a[8];
             for (int i = 0; i < 8; i++) a[i] = v[i];
@@ -53,4 +74,59 @@ extern "C" int fft_host(int n, int inv, float *io)
         }
     }
     return -1;
+}
+
+// ---- k_resample_q's per-thread stages (resample_q.cuh), one hop emulated thread by thread ----
+#define RQ_HOST_ONLY 1
+#include "../../odr-dabmod_b200/csrc/resample_q.cuh"
+#include <vector>
+#include <cmath>
+
+// F: 4096 spectrum bins (already scaled); tw_out: No roots e^{+j 2 pi i / No}; out: P*2000 samples
+extern "C" int rq_hop_host(int P, const float *F_, const float *tw_out_, float *out_)
+{
+    const float2 *Fin = reinterpret_cast<const float2 *>(F_);
+    const float2 *tw_out = reinterpret_cast<const float2 *>(tw_out_);
+    float2 *out = reinterpret_cast<float2 *>(out_);
+    const int no = P * RQ_Q;
+    std::vector<float2> itw2(5 * 20), itw3(4 * 400), buf(RQ_BUF), fold(RQ_NFOLD);
+    for (int i = 0; i < 5 * 20; i++) itw2[i] = tw_out[(((i % 20) << (i / 20)) % 400) * 10 * P];
+    for (int i = 0; i < 4 * 400; i++) itw3[i] = tw_out[(((i % 400) << (i / 400)) % 4000) * P];
+    for (int t = 0; t < RQ_NFOLD; t++) fold[t] = Fin[2048 + t];
+    std::vector<float2> regs(256 * 20);
+    for (int rho = 0; rho < P; rho++) {
+        for (auto &b : buf) b = make_float2(NAN, NAN);   // an unwritten slot poisons the result
+        for (int t = 0; t < 256; t++) {
+            float2 F[16];
+            for (int r = 0; r < 16; r++) F[r] = Fin[t + 256 * r];
+            const float2 fp7 = t >= 160 ? fold[t - 160] : make_float2(0.f, 0.f);
+            rq_spread(F, fp7, fold[RQ_NFOLD - 1], t, rho, no, tw_out, buf.data());
+        }
+        for (int t = 0; t < RQ_ACTIVE; t++) {
+            float2 v[20];
+            rq_pass1_load(buf.data(), t, v);
+            for (int r = 0; r < 20; r++) regs[t * 20 + r] = v[r];
+        }
+        for (int t = 0; t < RQ_ACTIVE; t++) {
+            float2 v[20];
+            for (int r = 0; r < 20; r++) v[r] = regs[t * 20 + r];
+            rq_pass1_store(buf.data(), t, v);
+        }
+        for (int t = 0; t < RQ_ACTIVE; t++) {
+            float2 v[20];
+            rq_pass2_load(buf.data(), itw2.data(), t, v);
+            for (int r = 0; r < 20; r++) regs[t * 20 + r] = v[r];
+        }
+        for (int t = 0; t < RQ_ACTIVE; t++) {
+            float2 v[20];
+            for (int r = 0; r < 20; r++) v[r] = regs[t * 20 + r];
+            rq_pass2_store(buf.data(), t, v);
+        }
+        for (int b = 0; b < 400; b++) {
+            float2 x[10];
+            rq_pass3(buf.data(), itw3.data(), b, x);
+            for (int r = 0; r < 5; r++) out[(size_t)(b + 400 * r) * P + rho] = x[r];
+        }
+    }
+    return 0;
 }

@@ -105,7 +105,8 @@ def test_errors(dm, rng):
 # ---------------------------------------------------------------------------
 # Resampler (Resampler.cpp:131-195): FFT overlap-add with state across TFs
 # ---------------------------------------------------------------------------
-RES_CASES = [(1, 8192000), (1, 10000000), (2, 4096000), (1, 1536000), (4, 2500000), (3, 2400000), (2, 3200000)]
+RES_CASES = [(1, 8192000), (1, 10000000), (2, 4096000), (1, 1536000), (4, 2500000), (3, 2400000), (2, 3200000),
+             (1, 4000000), (1, 6000000), (1, 8000000)]
 
 
 @pytest.mark.parametrize("mode,rate", RES_CASES)
@@ -140,6 +141,34 @@ def test_resampler_state_across_calls(dm, rng, mode, rate):
     tail = mod2.process_batch(bits[2:])
     for i in range(2):
         assert rel_rms(tail[i], ora[2 + i]) < TOL, i
+
+
+@pytest.mark.parametrize("rate,P", [(4000000, 2), (6000000, 3), (8000000, 4), (10000000, 5)])
+def test_resampler_q_kernel(dm, rng, rate, P):
+    """k_resample_q (TM I, No = P * 4000: phase transforms of 4000 points in shared memory) is the kernel that runs
+    for these rates, agrees with the oracle across calls and after seek(), and with the generic kernel."""
+    assert dm.resampler_sizes(2048000, rate, 2048) == (4096, 4000 * P)
+    bits = bits_for(rng, 1, 5)
+    ora = oracle.OracleChain(mode=1, output_rate=rate).run(bits)
+    mod = dm.Modulator(mode=1, output_rate=rate, max_batch=3)
+    mod.set_param("profile", 1)
+    got = list(mod.process_batch(bits[:3]))
+    assert "k_resample_q" in [k for k, _ in mod.kernel_times()]
+    got += [mod.process(bits[3]), mod.process(bits[4])]
+    for i in range(5):
+        assert got[i].size == 196608 * 4000 * P // 4096
+        assert rel_rms(got[i], ora[i]) < TOL, i
+    mod2 = dm.Modulator(mode=1, output_rate=rate, max_batch=3)
+    mod2.seek(3, bits[2])
+    for i, y in enumerate(mod2.process_batch(bits[3:])):
+        assert np.array_equal(y.view(np.uint32), got[3 + i].view(np.uint32)), i
+    gen = dm.Modulator(mode=1, output_rate=rate, max_batch=3)
+    gen.set_param("res_kernel", 0)
+    gen.set_param("profile", 1)
+    ref = gen.process_batch(bits[:3])
+    assert "k_resample" in [k for k, _ in gen.kernel_times()]
+    for i in range(3):
+        assert rel_rms(got[i], ref[i]) < 1e-6, i
 
 
 def test_resampler_unsupported_rate(dm):
