@@ -20,11 +20,13 @@
 // nothing leaves the SM but the result.
 //
 // A CTA is two teams of 256 threads, each on its own hop with its own buffers and
-// named barrier (200 threads of a team carry the 20-point butterflies).  The phases
-// 0..P-2 are staged in shared memory, the last one stays in the FFT buffer (the last
-// pass works in place on its own slots), and the
-// hop's P*2000 output samples go out interleaved as fully coalesced stores with the
-// MemlessPoly / FormatConverter epilogue.
+// named barrier (200 threads of a team carry the 20-point butterflies).  The phase
+// twiddles e^{j 2 pi k' rho / No} of a thread's 16 bins are a geometric sequence
+// (ratio e^{j 2 pi 256 rho / No}): one table value per thread and phase, the rest by
+// multiplication.  The phases 0..P-2 are staged in shared memory, the last one stays in
+// the FFT buffer (the last pass works in place on its own slots), and the hop's P*2000
+// output samples go out interleaved as fully coalesced stores with the MemlessPoly /
+// FormatConverter epilogue.
 //
 // The per-thread stages are plain functions over a `float2 *buf`; with DABMOD_FN
 // redefined they compile for the host, where tests/test_fft_host.py runs a whole hop
@@ -45,62 +47,74 @@ constexpr int RQ_MIN_P = 2, RQ_MAX_P = 5;
 constexpr int RQ_FOLD0 = RQ_Q - RQ_HI;        // 1952: first slot that receives two bins
 constexpr int RQ_NFOLD = RQ_HI - RQ_FOLD0 + 1; // 97
 constexpr int RQ_SHIFT = RQ_NI - RQ_Q;        // 96: slot of a negative bin = its FFT index - 96
-constexpr int RQ_STAGE_STRIDE = RQ_KEEP + RQ_KEEP / 20;  // pad20 layout like the FFT buffer
+constexpr int RQ_S1 = 201;                    // row stride of the layout between pass 1 and pass 2
+constexpr int RQ_S2 = 404;                    // row stride of the layout between pass 2 and pass 3, and of the results
+constexpr int RQ_STAGE_STRIDE = 5 * RQ_S2;    // one phase's 2000 results: element m at 404 (m / 400) + m % 400
+constexpr int RQ_BUF = RQ_NI + RQ_NI / 16;    // the forward transform's spad(4096); the layouts below need <= 4036
 
-// Shared-memory index padding for the radix-20 passes: one slot per 20 makes the
-// stride-20 writes of the first pass conflict free for 8-byte elements (stride 21).
-__device__ __host__ __forceinline__ constexpr int pad20(int i) { return i + i / 20; }
-constexpr int RQ_BUF = RQ_NI + RQ_NI / 16;    // >= pad20(4000) and the forward transform's spad(4096)
+// Shared-memory layouts of the 4000-point transform (8-byte elements, a half-warp is conflict free when its
+// 16 slots differ mod 16).  Every exchange has its own layout so that both sides are contiguous or odd-strided
+// without gaps (a padded natural order costs a second wavefront wherever a run of lanes crosses a pad slot):
+//   spread -> pass 1:  slot q                    stores: consecutive q;  loads: q = t + 200 r
+//   pass 1 -> pass 2:  element 20 t + r at 201 r + t         stores: consecutive t;  loads: 201 k + g + 10 r'
+//   pass 2 -> pass 3:  element 400 g + j at 404 g + j        stores: j = k + 20 r, k fastest over the lanes, the
+//                      next g continues the run mod 16 (404 = 4 mod 16, 20 = 4 mod 16);  loads: 404 r + b
+//   results:           X[400 r + b] at 404 r + b, in place on the slots the butterfly has just read
+__device__ __host__ __forceinline__ constexpr int rq_result_slot(int m) { return RQ_S2 * (m / 400) + m % 400; }
 
-#if defined(__CUDA_ARCH__)
-#define RQ_LDG(p) __ldg(p)
-#else
-#define RQ_LDG(p) (*(p))
-#endif
+// Per-phase uniform constants (shared memory, RqPhase ph[P]): c = w^(256 rho), d = w^(-160 rho), e = w^(96 rho),
+// w = e^{+j 2 pi / No}
+struct RqPhase { float2 c, d, e; float2 pad_; };
 
-// e^{+j 2 pi e / No} for a signed exponent |e| < No
-DABMOD_FN float2 rq_root(const float2 *tw_out, int no, int e)
+// G_rho into buf (natural order).  Thread t holds F[t + 256 r] in F[r]; fp7 / fp8 are the bins that
+// fold onto its slots 1792 + t (t >= 160) and 2048 (t == 0): F[k + 96].  wt = w^(t rho).  The twiddles
+// w^(k' rho) of the thread's 16 bins k' = t + 256 r (r < 8), t + 256 (r - 16) (r >= 8) follow from wt by
+// repeated multiplication with c resp. its conjugate: no table look-ups in the loop.
+template <bool FIRST>
+DABMOD_FN void rq_spread(const float2 (&F)[16], float2 fp7, float2 fp8, int t, float2 wt, const RqPhase &ph,
+                         float2 *buf)
 {
-    return RQ_LDG(tw_out + (e < 0 ? e + no : e));
-}
-
-// G_rho into buf (natural order, pad20).  Thread t holds F[t + 256 r] in F[r]; fp7 / fp8 are the
-// bins that fold onto its slots 1792 + t (t >= 160) and 2048 (t == 0): F[k + 96].
-DABMOD_FN void rq_spread(const float2 (&F)[16], float2 fp7, float2 fp8, int t, int rho, int no,
-                         const float2 *tw_out, float2 *buf)
-{
+    if (FIRST) {                              // rho = 0: all twiddles are 1
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const int k = t + 256 * r;
-        if (r < 8) {                          // k' = k >= 0, slot k
+        for (int r = 0; r < 8; r++) {
             float2 g = F[r];
-            if (rho) g = cmul(g, rq_root(tw_out, no, k * rho));
-            if (r == 7 && t >= 160) {         // slot >= 1952: plus the bin k' = k - 4000
-                float2 h = fp7;
-                if (rho) h = cmul(h, rq_root(tw_out, no, (k - RQ_Q) * rho));
-                g = cadd(g, h);
+            if (r == 7 && t >= 160) g = cadd(g, fp7);
+            buf[t + 256 * r] = g;
+        }
+#pragma unroll
+        for (int r = 8; r < 16; r++) {
+            if (r == 8 && t < RQ_NFOLD) {
+                if (t == 0) buf[RQ_HI] = cadd(F[8], fp8);
             }
-            buf[pad20(k)] = g;
+            else buf[t + 256 * r - RQ_SHIFT] = F[r];
         }
-        else if (r == 8 && t <= RQ_NFOLD - 1) {
-            // FFT indices 2048..2144: the Nyquist bin is also k' = +2048 (slot 2048, shared with
-            // k' = -1952 = FFT index 2144); as negative bins they are added by the owners of
-            // the slots 1952..2048 above.
-            if (t == 0) {
-                float2 g = F[8], h = fp8;
-                if (rho) {
-                    g = cmul(g, rq_root(tw_out, no, RQ_HI * rho));
-                    h = cmul(h, rq_root(tw_out, no, (RQ_HI - RQ_Q) * rho));
-                }
-                buf[pad20(RQ_HI)] = cadd(g, h);
-            }
-        }
-        else {                                // k' = k - 4096 < -1952, slot k' + 4000
-            float2 g = F[r];
-            if (rho) g = cmul(g, rq_root(tw_out, no, (k - RQ_NI) * rho));
-            buf[pad20(k - RQ_SHIFT)] = g;
-        }
+        return;
     }
+    const float2 c = ph.c, cc = make_float2(c.x, -c.y);
+    float2 root = wt;
+#pragma unroll
+    for (int r = 0; r < 7; r++) {             // k' = k = t + 256 r >= 0, slot k
+        buf[t + 256 * r] = cmul(F[r], root);
+        root = cmul(root, c);
+    }
+    float2 g7 = cmul(F[7], root);             // slots >= 1952 also receive the bin k' = k - 4000: below
+    root = cmul(wt, cc);                      // k' = t - 256
+#pragma unroll
+    for (int r = 15; r > 8; r--) {            // k' = k - 4096 < -1952, slot k' + 4000 = k - 96
+        buf[t + 256 * r - RQ_SHIFT] = cmul(F[r], root);
+        root = cmul(root, cc);
+    }
+    // root = w^((t - 2048) rho): FFT indices 2048..2303
+    if (t >= RQ_NFOLD) buf[t + 256 * 8 - RQ_SHIFT] = cmul(F[8], root);
+    else if (t == 0) {
+        // the Nyquist bin as k' = +2048 (twiddle = conjugate of w^(-2048 rho)) plus the bin k' = -1952 (FFT index 2144)
+        const float2 g = cmul(F[8], make_float2(root.x, -root.y));
+        const float2 h = cmul(fp8, cmul(root, ph.e));
+        buf[RQ_HI] = cadd(g, h);
+    }
+    // (FFT indices 2049..2144 are negative bins that fold: added by the owners of the slots 1953..2047 here)
+    if (t >= 160) g7 = cadd(g7, cmul(fp7, cmul(root, ph.d)));   // k' = (t - 2048) - 160
+    buf[t + 256 * 7] = g7;
 }
 
 // twiddle powers w^r from the tabled w^(2^i): tab[i * Ns + k]
@@ -118,24 +132,22 @@ DABMOD_FN void rq_powers20(const float2 *tab, int k, float2 (&w)[20])
 // pass 1, butterfly t < 200: x[t + 200 r] -> 20-point transform (no twiddles)
 DABMOD_FN void rq_pass1_load(const float2 *buf, int t, float2 (&v)[20])
 {
-    const float2 *src = buf + pad20(t);        // pad20(t + 200 r) = pad20(t) + 210 r
 #pragma unroll
-    for (int r = 0; r < 20; r++) v[r] = src[210 * r];
+    for (int r = 0; r < 20; r++) v[r] = buf[t + 200 * r];
     fft20<true>(v);
 }
 DABMOD_FN void rq_pass1_store(float2 *buf, int t, const float2 (&v)[20])
 {
-    float2 *dst = buf + 21 * t;                // pad20(20 t + r) = 21 t + r
 #pragma unroll
-    for (int r = 0; r < 20; r++) dst[r] = v[r];
+    for (int r = 0; r < 20; r++) buf[RQ_S1 * r + t] = v[r];
 }
-// pass 2, butterfly t < 200, k = t mod 20: twiddles e^{+j 2 pi k r / 400}
+// pass 2, butterfly t = 20 g + k < 200: elements t + 200 r' = 20 (g + 10 r') + k, twiddles e^{+j 2 pi k r' / 400}
 DABMOD_FN void rq_pass2_load(const float2 *buf, const float2 *itw2, int t, float2 (&v)[20])
 {
-    const int k = t % 20;
-    const float2 *src = buf + pad20(t);
+    const int g = t / 20, k = t - 20 * g;
+    const float2 *src = buf + RQ_S1 * k + g;
 #pragma unroll
-    for (int r = 0; r < 20; r++) v[r] = src[210 * r];
+    for (int r = 0; r < 20; r++) v[r] = src[10 * r];
     float2 w[20];
     rq_powers20(itw2, k, w);
 #pragma unroll
@@ -145,16 +157,16 @@ DABMOD_FN void rq_pass2_load(const float2 *buf, const float2 *itw2, int t, float
 DABMOD_FN void rq_pass2_store(float2 *buf, int t, const float2 (&v)[20])
 {
     const int g = t / 20, k = t - 20 * g;
-    float2 *dst = buf + 420 * g + k;           // pad20(400 g + k + 20 r) = 420 g + k + 21 r
+    float2 *dst = buf + RQ_S2 * g + k;        // element 400 g + k + 20 r
 #pragma unroll
-    for (int r = 0; r < 20; r++) dst[21 * r] = v[r];
+    for (int r = 0; r < 20; r++) dst[20 * r] = v[r];
 }
-// pass 3, butterfly b < 400 (k = b): twiddles e^{+j 2 pi k r / 4000}; x[r] = X[b + 400 r], r < 5
+// pass 3, butterfly b < 400 (k = b): elements b + 400 r, twiddles e^{+j 2 pi k r / 4000};
+// on return x[r] = X[b + 400 r], r < 5, to be stored at dst[404 r + b]
 DABMOD_FN void rq_pass3(const float2 *buf, const float2 *itw3, int b, float2 (&x)[10])
 {
-    const float2 *src = buf + pad20(b);        // pad20(b + 400 r) = pad20(b) + 420 r
 #pragma unroll
-    for (int r = 0; r < 10; r++) x[r] = src[420 * r];
+    for (int r = 0; r < 10; r++) x[r] = buf[RQ_S2 * r + b];
     const float2 w1 = itw3[b], w2 = itw3[400 + b], w4 = itw3[800 + b], w8 = itw3[1200 + b];
     const float2 w3 = cmul(w1, w2);
     x[1] = cmul(x[1], w1); x[2] = cmul(x[2], w2); x[3] = cmul(x[3], w3); x[4] = cmul(x[4], w4);
@@ -179,6 +191,7 @@ struct RqSmem {
     float2 tw3[4 * 256];
     float2 itw2[5 * 20];                      // itw2[i*20 + k]  = e^{+j 2 pi k 2^i / 400}
     float2 itw3[4 * 400];                     // itw3[i*400 + k] = e^{+j 2 pi k 2^i / 4000}
+    RqPhase ph[RQ_MAX_P];                     // per-phase twiddle constants
     float2 fold[RQ_TEAMS][RQ_NFOLD + 1];      // F[2048 .. 2144] of the team's current hop
     float2 buf[RQ_TEAMS][RQ_BUF];
     float2 stage[RQ_TEAMS][RQ_MAX_P - 1][RQ_STAGE_STRIDE];  // phase rho < P-1 at [rho][m]; phase P-1 ends in buf
@@ -204,6 +217,12 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
     for (int i = tid; i < 4 * 256; i += RQ_THREADS) sm.tw3[i] = __ldg(p.tw_in + (((i & 255) << (i >> 8)) & (RQ_NI - 1)));
     for (int i = tid; i < 5 * 20; i += RQ_THREADS) sm.itw2[i] = __ldg(p.tw_out + (((i % 20) << (i / 20)) % 400) * 10 * P);
     for (int i = tid; i < 4 * 400; i += RQ_THREADS) sm.itw3[i] = __ldg(p.tw_out + (((i % 400) << (i / 400)) % 4000) * P);
+    if (tid < P) {
+        const int rho = tid;
+        sm.ph[rho].c = __ldg(p.tw_out + 256 * rho);
+        sm.ph[rho].d = __ldg(p.tw_out + (no - 160 * rho) % no);
+        sm.ph[rho].e = __ldg(p.tw_out + 96 * rho);
+    }
     __syncthreads();
 
     float2 *buf = sm.buf[team];
@@ -253,9 +272,14 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
         const float2 fp7 = t >= 160 ? sm.fold[team][t - 160] : make_float2(0.f, 0.f);
         const float2 fp8 = sm.fold[team][RQ_NFOLD - 1];
 
+        float2 wt = __ldg(p.tw_out + t);      // w^(t rho) of the next phase, fetched one phase ahead
         for (int rho = 0; rho < P; rho++) {
             ru_bar(team);                     // the previous user of buf is done reading
-            rq_spread(F, fp7, fp8, t, rho, no, p.tw_out, buf);
+            if (rho == 0) rq_spread<true>(F, fp7, fp8, t, wt, sm.ph[0], buf);
+            else {
+                rq_spread<false>(F, fp7, fp8, t, wt, sm.ph[rho], buf);
+                wt = __ldg(p.tw_out + t * (rho + 1));   // < 256 * 5 entries: stays in L1
+            }
             ru_bar(team);
             float2 v[20];
             if (t < RQ_ACTIVE) rq_pass1_load(buf, t, v);
@@ -274,7 +298,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
                     float2 x[10];
                     rq_pass3(buf, sm.itw3, t + 200 * u, x);
 #pragma unroll
-                    for (int r = 0; r < 5; r++) dst[pad20(t + 200 * u) + 420 * r] = x[r];
+                    for (int r = 0; r < 5; r++) dst[RQ_S2 * r + t + 200 * u] = x[r];
                 }
             }
         }
@@ -285,7 +309,7 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
             const size_t obase = (size_t)hop * n_out;
             for (int e = t; e < n_out; e += RQ_TEAM) {
                 const int m = e / P, rho = e - m * P;
-                const float2 y = (rho == P - 1 ? buf : sm.stage[team][rho])[pad20(m)];
+                const float2 y = (rho == P - 1 ? buf : sm.stage[team][rho])[rq_result_slot(m)];
                 store_sample<POST>(p.out, obase + e, y, p.post, clip);
             }
         }

@@ -96,11 +96,16 @@ extern "C" int rq_hop_host(int P, const float *F_, const float *tw_out_, float *
     std::vector<float2> regs(256 * 20);
     for (int rho = 0; rho < P; rho++) {
         for (auto &b : buf) b = make_float2(NAN, NAN);   // an unwritten slot poisons the result
+        RqPhase ph;
+        ph.c = tw_out[256 * rho];
+        ph.d = tw_out[(no - 160 * rho) % no];
+        ph.e = tw_out[96 * rho];
         for (int t = 0; t < 256; t++) {
             float2 F[16];
             for (int r = 0; r < 16; r++) F[r] = Fin[t + 256 * r];
             const float2 fp7 = t >= 160 ? fold[t - 160] : make_float2(0.f, 0.f);
-            rq_spread(F, fp7, fold[RQ_NFOLD - 1], t, rho, no, tw_out, buf.data());
+            if (rho == 0) rq_spread<true>(F, fp7, fold[RQ_NFOLD - 1], t, tw_out[0], ph, buf.data());
+            else rq_spread<false>(F, fp7, fold[RQ_NFOLD - 1], t, tw_out[t * rho], ph, buf.data());
         }
         for (int t = 0; t < RQ_ACTIVE; t++) {
             float2 v[20];
@@ -125,7 +130,10 @@ extern "C" int rq_hop_host(int P, const float *F_, const float *tw_out_, float *
         for (int b = 0; b < 400; b++) {
             float2 x[10];
             rq_pass3(buf.data(), itw3.data(), b, x);
-            for (int r = 0; r < 5; r++) out[(size_t)(b + 400 * r) * P + rho] = x[r];
+            for (int r = 0; r < 5; r++) buf[RQ_S2 * r + b] = x[r];   // in place, like the last phase
+        }
+        for (int m = 0; m < RQ_KEEP; m++) {
+            out[(size_t)m * P + rho] = buf[rq_result_slot(m)];
         }
     }
     return 0;
