@@ -179,18 +179,28 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
                 sm.stage[team][0][t + 256 * r] = make_float2(y.x * p.factor, y.y * p.factor);
             }
         }
+        float2 wt = __ldg(p.tw_out + t);      // e^{j 2 pi t rho / No} of the next phase, fetched one phase ahead
         for (int rho = 1; rho < L; rho++) {
-            // G_rho[k] = F[k] e^{j 2 pi k' rho / No}; tw_out[i] = e^{+j 2 pi i / No}
+            // G_rho[k] = F[k] e^{j 2 pi k' rho / No}, tw_out[i] = e^{+j 2 pi i / No}.  The thread's bins are
+            // k' = t + 256 r (r < 8) and t + 256 (r - 16) (r >= 8): a geometric sequence in r with ratio
+            // c = e^{j 2 pi 256 rho / No} -- one table value per phase, the rest by multiplication.
+            const float2 c = __ldg(p.tw_out + 256 * rho), cc = make_float2(c.x, -c.y);
+            float2 root = wt;
 #pragma unroll
-            for (int r = 0; r < 16; r++) {
-                const int k = t + 256 * r;
-                const int ks = k < hi ? k : k - RU_NI;
-                int e = ks * rho;                 // |k' rho| < Ni/2 * L = No/2: no reduction needed
-                if (e < 0) e += no;
-                float2 w = __ldg(p.tw_out + e);
-                if (k == hi) w = make_float2(w.x + w.x, 0.f);   // e^{+j a} + e^{-j a} = 2 cos a
-                v[r] = cmul(F[r], w);
+            for (int r = 0; r < 8; r++) {
+                v[r] = cmul(F[r], root);
+                root = cmul(root, c);
             }
+            root = cmul(wt, cc);
+#pragma unroll
+            for (int r = 15; r > 8; r--) {
+                v[r] = cmul(F[r], root);
+                root = cmul(root, cc);
+            }
+            // r = 8: k' = t - 2048; bin Ni/2 (t = 0) sits on both sides: e^{+j a} + e^{-j a} = 2 cos a
+            if (t == 0) root = make_float2(root.x + root.x, 0.f);
+            v[8] = cmul(F[8], root);
+            wt = __ldg(p.tw_out + t * (rho + 1));
             ru_fft4096<true>(v, buf, sm.tw2, sm.tw3, t, team);
 #pragma unroll
             for (int r = 0; r < 8; r++)
