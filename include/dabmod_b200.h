@@ -136,6 +136,10 @@ int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits
  *   "digital", "mode" (fix|max|var), "var"      GainControl.cpp:520-603
  *   "windowlen"                                 GuardIntervalInserter.cpp:338-379
  *   "cfr", "clip", "errorclip"                  OfdmGenerator.cpp:376-404
+ *   "clip_stats", "papr" (read-only)            OfdmGenerator.cpp:419-453: the same strings the reference
+ *                                               prints, from per-symbol records written by the symbol kernel
+ *                                               (clip / error-clip ratios and MER over the last 10 frames,
+ *                                               PAPR before / after CFR over the last 50 frames' symbols)
  *   "enable", "comb", "pattern", "old_variant"  TII.cpp:339-376 (prefixed "tii." here)
  * plus "taps" (count, then taps, whitespace separated: FIRFilter tapsfile
  * content) and "coefs" (MemlessPoly coefficient-file content).

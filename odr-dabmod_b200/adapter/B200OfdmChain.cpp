@@ -108,7 +108,8 @@ B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format,
 
     if (dabmod_b200_create(&c, &m_handle) != DABMOD_B200_OK) fail("create");
 
-    /* names of the replaced blocks' parameters (GainControl.cpp:520-603, TII.cpp:339-376) */
+    /* names of the replaced blocks' parameters (GainControl.cpp:520-603, TII.cpp:339-376,
+     * OfdmGenerator.cpp:63-67, GuardIntervalInserter.cpp:100-103) */
     const char* params[][2] = {
         {"digital", "Digital Gain"},
         {"mode", "Gainmode (fix|max|var)"},
@@ -117,6 +118,12 @@ B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format,
         {"tii.comb", "TII comb number [0-23]"},
         {"tii.pattern", "TII pattern number [0-69]"},
         {"tii.old_variant", "select old TII variant for old (buggy) receivers"},
+        {"windowlen", "Window length for OFDM windowng [0 to disable]"},
+        {"cfr", "Enable crest factor reduction"},
+        {"clip", "CFR: Clip to amplitude"},
+        {"errorclip", "CFR: Limit error"},
+        {"clip_stats", "CFR: statistics (clip ratio, errorclip ratio)"},
+        {"papr", "PAPR measurements (before CFR, after CFR)"},
         {"taps", "FIR taps: count followed by the taps"},
         {"coefs", "Predistorter coefficient file content"},
     };

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <sstream>
@@ -79,6 +80,97 @@ size_t format_bytes(int fmt)
     }
 }
 
+// PAPRStats.cpp:36-107: peak-to-average power ratio over a sliding window of blocks (symbols)
+struct PaprWindow {
+    size_t n_blocks = 0;
+    std::deque<double> peaks, means;
+    void add(double peak, double mean)
+    {
+        peaks.push_back(peak);
+        means.push_back(mean);
+        if (means.size() > n_blocks) { means.pop_front(); peaks.pop_front(); }
+    }
+    double papr() const
+    {
+        if (means.size() < n_blocks) return 0;
+        double peak = 0, rms2 = 0;
+        for (size_t i = 0; i < peaks.size(); i++) {
+            if (peaks[i] > peak) peak = peaks[i];
+            rms2 += means[i];
+        }
+        rms2 /= (double)peaks.size();
+        return 10.0 * std::log10(peak / rms2);
+    }
+    void clear() { peaks.clear(); means.clear(); }
+};
+
+// Host side of the CFR read-outs (OfdmGenerator.cpp:186-306, 419-453): fed with the per-symbol
+// records the symbol kernel writes, one transmission frame at a time, in stream order.
+struct CfrReadouts {
+    static constexpr size_t MAX_CLIP_STATS = 10;      // OfdmGenerator.cpp:38
+    PaprWindow before, after;
+    std::deque<double> clip_ratios, errclip_ratios, mers;
+    size_t mer_index = 0;
+    bool clear_request = false;
+
+    void init(int n_sym)
+    {
+        before = PaprWindow{};
+        after = PaprWindow{};
+        before.n_blocks = after.n_blocks = (size_t)n_sym * 50;    // OfdmGenerator.cpp:59-61
+        clip_ratios.clear(); errclip_ratios.clear(); mers.clear();
+        mer_index = 0;
+        clear_request = false;
+    }
+    void add_frame(const CfrSymStat *rec, int n_sym, int N)
+    {
+        mer_index = (mer_index + 1) % (size_t)n_sym;
+        if (clear_request) { before.clear(); after.clear(); clear_request = false; }
+        size_t num_clip = 0, num_err = 0;
+        for (int i = 0; i < n_sym; i++) {
+            const CfrSymStat &r = rec[i];
+            before.add(r.peak_before, (double)r.sum_before / N);
+            if (i > 0) after.add(r.peak_after, (double)r.sum_after / N);
+            if (i > 0 && mer_index == (size_t)i) {
+                // ETSI ETR 290 annex C; by Parseval the time-domain sums of the reference
+                // (OfdmGenerator.cpp:262-271) are N times these frequency-domain sums
+                mers.push_back(r.sum_delta > 0 ? 10.0 * std::log10((double)r.sum_ref / (double)r.sum_delta) : 90);
+            }
+            num_clip += r.clip;
+            num_err += r.errclip;
+        }
+        const double n_samps = (double)n_sym * N;
+        clip_ratios.push_back((double)num_clip / n_samps);
+        errclip_ratios.push_back((double)num_err / n_samps);
+        while (clip_ratios.size() > MAX_CLIP_STATS) clip_ratios.pop_front();
+        while (errclip_ratios.size() > MAX_CLIP_STATS) errclip_ratios.pop_front();
+        while (mers.size() > MAX_CLIP_STATS) mers.pop_front();
+    }
+    static double avg(const std::deque<double> &d)
+    {
+        double a = 0;
+        for (double v : d) a += v;
+        return a / (double)d.size();
+    }
+    std::string clip_stats() const      // OfdmGenerator.cpp:420-441
+    {
+        std::stringstream ss;
+        if (clip_ratios.empty() || errclip_ratios.empty() || mers.empty()) ss << "No stats available";
+        else
+            ss << "Statistics : " << std::fixed << avg(clip_ratios) * 100 << "% samples clipped, "
+               << avg(errclip_ratios) * 100 << "% errors clipped. MER after CFR: " << avg(mers) << " dB";
+        return ss.str();
+    }
+    std::string papr() const            // OfdmGenerator.cpp:443-452
+    {
+        const double b = before.papr(), a = after.papr();
+        std::stringstream ss;
+        ss << "PAPR [dB]: " << std::fixed << (b == 0 ? std::string("N/A") : std::to_string(b)) << ", "
+           << (a == 0 ? std::string("N/A") : std::to_string(a));
+        return ss.str();
+    }
+};
+
 } // namespace
 
 struct dabmod_b200 {
@@ -137,6 +229,13 @@ struct dabmod_b200 {
 
     uint64_t clipped_last = 0;
     uint32_t launches_last = 0;
+
+    // CFR read-outs ("clip_stats", "papr"): per-symbol records of the last launch, aggregated on the host
+    DevBuf<CfrSymStat> d_cfr_stats;
+    CfrReadouts cfr_readouts;
+    bool cfr_collect = true;       // false while seek() re-runs a frame that is not part of this handle's range
+    size_t cfr_pending = 0;        // TFs whose records wait in d_cfr_stats
+    cudaStream_t cfr_stream = nullptr;
 
     // optional per-kernel timing
     bool profile = false;
@@ -307,6 +406,20 @@ bool fft_radices(int n, std::vector<unsigned char> &rad)
 }
 
 // symbols [-> FIR]: d_bits -> dst (float2 stream, or the final format when `last`)
+// Fetch the CFR records of the frames processed since the last call and feed the read-outs.
+void consume_cfr(dabmod_b200 *h)
+{
+    if (!h->cfr_pending) return;
+    const size_t n_sym = (size_t)h->m.L + 1;
+    std::vector<CfrSymStat> rec(h->cfr_pending * n_sym);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    CUDA_CHECK(cudaStreamSynchronize(h->cfr_stream));
+    CUDA_CHECK(cudaMemcpy(rec.data(), h->d_cfr_stats.p, rec.size() * sizeof(CfrSymStat), cudaMemcpyDeviceToHost));
+    for (size_t tf = 0; tf < h->cfr_pending; tf++)
+        h->cfr_readouts.add_frame(rec.data() + tf * n_sym, (int)n_sym, h->m.N);
+    h->cfr_pending = 0;
+}
+
 void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst, bool last, size_t tmp_tf0,
                    uint64_t stream_tf, cudaStream_t s, uint32_t &launches)
 {
@@ -344,6 +457,13 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     sp.cfr = c.cfr_enable;
     sp.cfr_clip = c.cfr_clip;
     sp.cfr_errclip = c.cfr_errclip;
+    sp.cfr_stats = nullptr;
+    if (c.cfr_enable && h->cfr_collect) {
+        if (!h->d_cfr_stats.p) h->d_cfr_stats.alloc((size_t)c.max_batch * (m.L + 1));
+        sp.cfr_stats = h->d_cfr_stats.p + tmp_tf0 * (size_t)(m.L + 1);
+        h->cfr_pending = std::max(h->cfr_pending, tmp_tf0 + n_tf);
+        h->cfr_stream = s;
+    }
     sp.gain_mode = c.gain_mode;
     sp.gain_const = c.normalise * c.digital_gain;
     sp.var_factor = c.gain_variance;
@@ -649,6 +769,7 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
         h->d_clipped.alloc(1);
         CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
         build_tables(h);
+        h->cfr_readouts.init(h->m.L + 1);
 
         const size_t nb = (size_t)h->cfg.max_batch;
         if (h->cfg.output_rate != 2048000) {
@@ -742,6 +863,7 @@ int dabmod_b200_process_batch_device(dabmod_b200 *h, const uint8_t *d_bits, size
         h->timed.clear();
         h->events_used = 0;
         if (n_tf == 0) return;
+        consume_cfr(h);      // the records of the previous launch, before this one overwrites them
         if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
             CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), s));
         enqueue(h, d_bits, n_tf, d_iq_out, 0, h->tf_counter, s, h->launches_last);
@@ -766,6 +888,7 @@ int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, 
         h->timed.clear();
         h->events_used = 0;
         if (n_tf == 0) return;
+        consume_cfr(h);
         if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
             CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
 
@@ -800,6 +923,7 @@ int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, 
             h->clipped_last = v;
         }
         CUDA_CHECK(cudaStreamSynchronize(h->s_out));
+        consume_cfr(h);
         h->tf_counter += n_tf;
         if (out_bytes) *out_bytes = n_tf * out_tf;
     });
@@ -834,6 +958,8 @@ int dabmod_b200_reset(dabmod_b200 *h)
         if (!h) throw ApiError(DABMOD_B200_EINVAL, "null handle");
         std::lock_guard<std::mutex> lock(h->mtx);
         h->tf_counter = 0;
+        consume_cfr(h);
+        h->cfr_readouts.init(h->m.L + 1);
         if (h->has_res) {
             CUDA_CHECK(cudaSetDevice(h->device));
             CUDA_CHECK(cudaMemsetAsync(h->d_hist.p, 0, sizeof(float2) * h->rp.ni, h->s_compute));
@@ -862,7 +988,16 @@ int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits
             CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p, prev_bits, nbytes, cudaMemcpyHostToDevice, s));
             float2 *front = h->has_fir() ? h->d_tmp2.p : h->d_tmp.p;
             uint32_t launches = 0;
-            enqueue_front(h, h->d_bits.p, 1, front, false, 0, tf_index - 1, s, launches);
+            consume_cfr(h);
+            h->cfr_collect = false;           // the halo frame belongs to the previous shard's read-outs
+            try {
+                enqueue_front(h, h->d_bits.p, 1, front, false, 0, tf_index - 1, s, launches);
+            }
+            catch (...) {
+                h->cfr_collect = true;
+                throw;
+            }
+            h->cfr_collect = true;
             CUDA_CHECK(cudaMemcpyAsync(h->d_hist.p, front + h->m.tf_samples - h->rp.ni, sizeof(float2) * h->rp.ni,
                                        cudaMemcpyDeviceToDevice, s));
         }
@@ -904,9 +1039,12 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
                 check_window(c.mode, v);
                 c.window_overlap = v; h->tables_dirty = true;
             }
-            else if (n == "cfr") { int v; ss >> v; c.cfr_enable = v != 0; }
-            else if (n == "clip") { ss >> c.cfr_clip; }
-            else if (n == "errorclip") { ss >> c.cfr_errclip; }
+            // (each of the three also restarts the PAPR windows: OfdmGenerator.cpp:384-395)
+            else if (n == "cfr") { int v; ss >> v; consume_cfr(h); c.cfr_enable = v != 0; h->cfr_readouts.clear_request = true; }
+            else if (n == "clip") { consume_cfr(h); ss >> c.cfr_clip; h->cfr_readouts.clear_request = true; }
+            else if (n == "errorclip") { consume_cfr(h); ss >> c.cfr_errclip; h->cfr_readouts.clear_request = true; }
+            else if (n == "clip_stats" || n == "papr")
+                throw ApiError(DABMOD_B200_EINVAL, "Parameter '" + n + "' is read-only");
             else if (n == "tii.enable") { int v; ss >> v; c.tii_enable = v != 0; h->tables_dirty = true; }
             else if (n == "tii.comb") {
                 int v; ss >> v;
@@ -969,6 +1107,8 @@ int dabmod_b200_get_param(dabmod_b200 *h, const char *name, char *buf, size_t ca
         else if (n == "cfr") ss << c.cfr_enable;
         else if (n == "clip") ss << std::fixed << c.cfr_clip;
         else if (n == "errorclip") ss << std::fixed << c.cfr_errclip;
+        else if (n == "clip_stats") { consume_cfr(h); ss << h->cfr_readouts.clip_stats(); }
+        else if (n == "papr") { consume_cfr(h); ss << h->cfr_readouts.papr(); }
         else if (n == "tii.enable") ss << (c.tii_enable ? 1 : 0);
         else if (n == "tii.comb") ss << c.tii_comb;
         else if (n == "tii.pattern") ss << c.tii_pattern;

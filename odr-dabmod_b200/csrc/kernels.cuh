@@ -132,6 +132,15 @@ __device__ __forceinline__ void flush_clip(const PostParams &pp, unsigned clip)
 // point shared buffer, so every mode keeps all 128 threads busy with 16
 // points each.
 // ---------------------------------------------------------------------------
+// Per-symbol statistics of the CFR block (OfdmGenerator.cpp:228-275): what the reference feeds to its
+// PAPRStats / clip ratio / MER read-outs ("papr", "clip_stats" remote-control parameters).
+struct CfrSymStat {
+    float peak_before, sum_before;   // max and sum of |x|^2 over the N samples after the first IFFT
+    float peak_after, sum_after;     // the same after the CFR iteration
+    float sum_ref, sum_delta;        // sum |X_ref|^2 and sum |X_out - X_ref|^2 over the bins (MER, by Parseval)
+    unsigned clip, errclip;          // clipped samples / clipped error bins
+};
+
 struct SymParams {
     // mode
     int L, K, N, null_size, sym_size, tf_in_bytes, tf_samples;
@@ -153,6 +162,7 @@ struct SymParams {
     // CFR
     int cfr;
     float cfr_clip, cfr_errclip;
+    CfrSymStat *cfr_stats;        // (L+1) records per TF of this launch, or nullptr
     // gain
     int gain_mode;
     float gain_const;             // normalise * digital_gain
@@ -181,7 +191,34 @@ struct SymSmemOpt {
     float2 ref[SYM_BUF];            // frequency-domain symbols as fed to the IFFT (CFR reference)
     float2 tail[2][MAX_WINDOW];     // windowed falling edge of the previous symbol, double buffered
     float win[MAX_WINDOW];          // rising edge, 2W entries
+    float stat[3][4][8][4];         // CFR statistics: [phase][warp][symbol in group][field] partial results
 };
+
+// Reduce per-thread partials of the G symbols of a group over the warp and park them in shared memory
+// (every lane of a warp looks at the same symbol for a given element index, see the CFR loops).
+template <int G>
+__device__ __forceinline__ void cfr_stat_warp(float (*dst)[8][4], int tid, const float (&mx)[G], const float (&sum1)[G],
+                                              const float (&sum2)[G], const unsigned (&cnt)[G])
+{
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(mx[g]));   // non-negative floats order like uints
+        const unsigned c = __reduce_add_sync(0xffffffffu, cnt[g]);
+        float a = sum1[g], b = sum2[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+            dst[warp][g][0] = __uint_as_float(m);
+            dst[warp][g][1] = a;
+            dst[warp][g][2] = b;
+            dst[warp][g][3] = __uint_as_float(c);
+        }
+    }
+}
 
 // out-position of symbol s inside the TF
 __device__ __forceinline__ int sym_pos(const SymParams &p, int s)
@@ -342,6 +379,7 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
             continue;
         }
         const int s0 = grp * G;   // first symbol of the group
+        const bool stats_on = OPT && cfr && what == EMIT && p.cfr_stats != nullptr;
         // ---- 1. frequency-domain symbols into the shared buffer ----
         // zero bins: DC and the guard band (OfdmGenerator.cpp:207-220)
         {
@@ -406,21 +444,44 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
             sym_fft<N, true>(sm.buf, sm.tw, tid);
             if (cfr) {
                 // ---- 2'. one CFR iteration (OfdmGenerator.cpp:310-373) ----
+                // Element tid + 128 i belongs to symbol i / (16 / G) of the group for every thread, so the
+                // statistics are G compile-time indexed partials per thread.
                 const float clip_sq = p.cfr_clip * p.cfr_clip;
                 const float err_sq = p.cfr_errclip * p.cfr_errclip;
+                float st_mx[G], st_a[G], st_b[G];
+                unsigned st_n[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) { st_mx[g] = 0.f; st_a[g] = 0.f; st_b[g] = 0.f; st_n[g] = 0; }
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const int e = spad(tid + SYM_THREADS * i);
                     float2 v = sm.buf[e];
                     const float mag = v.x * v.x + v.y * v.y;
+                    st_mx[i / (16 / G)] = fmaxf(st_mx[i / (16 / G)], mag);
+                    st_a[i / (16 / G)] += mag;
                     if (mag > clip_sq) {
                         const float f = sqrtf(clip_sq / mag);
                         v.x *= f; v.y *= f;
                         sm.buf[e] = v;
+                        st_n[i / (16 / G)]++;
                     }
                 }
+                if (stats_on) cfr_stat_warp<G>(so.stat[0], tid, st_mx, st_a, st_b, st_n);
                 __syncthreads();
+                if (stats_on && tid < G && s0 + tid <= p.L) {
+                    CfrSymStat &o = p.cfr_stats[(size_t)tf * (p.L + 1) + s0 + tid];
+                    float mx = 0.f, a = 0.f;
+                    unsigned c = 0;
+                    for (int w = 0; w < 4; w++) {
+                        mx = fmaxf(mx, so.stat[0][w][tid][0]);
+                        a += so.stat[0][w][tid][1];
+                        c += __float_as_uint(so.stat[0][w][tid][3]);
+                    }
+                    o.peak_before = mx; o.sum_before = a; o.clip = c;
+                }
                 sym_fft<N, false>(sm.buf, sm.tw, tid);
+#pragma unroll
+                for (int g = 0; g < G; g++) { st_a[g] = 0.f; st_b[g] = 0.f; st_n[g] = 0; }
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const int e = spad(tid + SYM_THREADS * i);
@@ -429,17 +490,66 @@ __global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__
                     const float2 r = so.ref[e];
                     float2 err = make_float2(r.x - pt.x, r.y - pt.y);
                     const float mag = err.x * err.x + err.y * err.y;
+                    st_a[i / (16 / G)] = fmaf(r.x, r.x, fmaf(r.y, r.y, st_a[i / (16 / G)]));
                     if (mag > err_sq) {
                         const float s = sqrtf(err_sq / mag);
                         err.x *= s; err.y *= s;
+                        // the bin moves by (1 - s) |error| away from the reference: the MER numerator
+                        st_b[i / (16 / G)] = fmaf(mag * (1.0f - s), 1.0f - s, st_b[i / (16 / G)]);
+                        st_n[i / (16 / G)]++;
                     }
                     sm.buf[e] = make_float2(pt.x + err.x, pt.y + err.y);
                 }
+                if (stats_on) cfr_stat_warp<G>(so.stat[1], tid, st_mx, st_a, st_b, st_n);
                 __syncthreads();
+                if (stats_on && tid < G && s0 + tid <= p.L) {
+                    CfrSymStat &o = p.cfr_stats[(size_t)tf * (p.L + 1) + s0 + tid];
+                    float a = 0.f, b = 0.f;
+                    unsigned c = 0;
+                    for (int w = 0; w < 4; w++) {
+                        a += so.stat[1][w][tid][1];
+                        b += so.stat[1][w][tid][2];
+                        c += __float_as_uint(so.stat[1][w][tid][3]);
+                    }
+                    o.sum_ref = a; o.sum_delta = b; o.errclip = c;
+                }
                 sym_fft<N, true>(sm.buf, sm.tw, tid);
             }
 #pragma unroll
             for (int i = 0; i < 16; i++) x[i] = sm.buf[spad(eg * N + tt + TG * i)];
+            if (stats_on) {
+                // PAPR after CFR: peak and mean power of the symbol this thread emits (TG threads per symbol)
+                constexpr int SL = TG < 32 ? TG : 32;
+                float mx = 0.f, a = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float mag = x[i].x * x[i].x + x[i].y * x[i].y;
+                    mx = fmaxf(mx, mag);
+                    a += mag;
+                }
+#pragma unroll
+                for (int o = SL / 2; o > 0; o >>= 1) {
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                }
+                const int lane = tid & 31;
+                if ((lane & (SL - 1)) == 0) {
+                    so.stat[2][tid >> 5][lane / SL][0] = mx;
+                    so.stat[2][tid >> 5][lane / SL][1] = a;
+                }
+                __syncthreads();
+                if (tid < G && s0 + tid <= p.L) {
+                    constexpr int WPS_ = TG < 32 ? 1 : TG / 32, SPW_ = TG < 32 ? 32 / TG : 1;
+                    const int ww = TG < 32 ? tid / SPW_ : tid * WPS_, ss = TG < 32 ? tid % SPW_ : 0;
+                    float m2 = 0.f, a2 = 0.f;
+                    for (int w = 0; w < WPS_; w++) {
+                        m2 = fmaxf(m2, so.stat[2][ww + w][ss][0]);
+                        a2 += so.stat[2][ww + w][ss][1];
+                    }
+                    CfrSymStat &o = p.cfr_stats[(size_t)tf * (p.L + 1) + s0 + tid];
+                    o.peak_after = m2; o.sum_after = a2;
+                }
+            }
         }
         else if (N == 2048) {
             // Per-pass twiddle tables (see StockhamPass): pass 2 at sm.tw, pass 3 behind it.

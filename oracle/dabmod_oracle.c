@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 typedef struct { float re, im; } cf;
@@ -360,13 +361,37 @@ DABO_EXPORT void dabo_dft(int n, int sign, const double *in, double *out)
 /* in: nsym x K carriers, out: nsym x N samples.                             */
 /* cfr_stats (optional, 2 x uint64): clipped samples, clipped errors.        */
 /* ------------------------------------------------------------------------ */
+/* PAPRStats::process_block (src/PAPRStats.cpp:41-70): peak and mean of |x|^2 */
+static void papr_block(const cf *x, int n, double *peak, double *mean)
+{
+    double pk = 0, rms2 = 0;
+    for (int i = 0; i < n; i++) {
+        const double v = (double)(x[i].re * x[i].re + x[i].im * x[i].im);   /* std::norm of a complexf */
+        if (v > pk) pk = v;
+        rms2 += v;
+    }
+    *peak = pk; *mean = rms2 / n;
+}
+
+/* sym_stats (optional, 8 doubles per symbol, CFR only; OfdmGenerator.cpp:228-275): peak and mean power
+ * before CFR, the same after, sum |before|^2, sum |after - before|^2 (MER), clipped samples, clipped errors */
+#define DABO_SYM_STATS 8
+DABO_EXPORT void dabo_ofdm_stats(const dabo_mode *m, const cf *in, int nsym, int cfr, float clip,
+                                 float errclip, cf *out, uint64_t *cfr_stats, double *sym_stats);
+
 DABO_EXPORT void dabo_ofdm(const dabo_mode *m, const cf *in, int nsym, int cfr, float clip,
                            float errclip, cf *out, uint64_t *cfr_stats)
+{
+    dabo_ofdm_stats(m, in, nsym, cfr, clip, errclip, out, cfr_stats, NULL);
+}
+
+DABO_EXPORT void dabo_ofdm_stats(const dabo_mode *m, const cf *in, int nsym, int cfr, float clip,
+                                 float errclip, cf *out, uint64_t *cfr_stats, double *sym_stats)
 {
     const int N = m->N, K = m->K;
     dft_plan *p = dft_plan_new(N);
     cd *X = malloc(sizeof(cd) * N), *x = malloc(sizeof(cd) * N);
-    cf *Xf = malloc(sizeof(cf) * N), *sym = malloc(sizeof(cf) * N);
+    cf *Xf = malloc(sizeof(cf) * N), *sym = malloc(sizeof(cf) * N), *before = malloc(sizeof(cf) * N);
     const int pos_dst = (K & 1) ? 0 : 1, pos_size = (K + 1) / 2;
     const int neg_dst = N - K / 2, neg_src = (K + 1) / 2, neg_size = K / 2;
     uint64_t nclip = 0, nerr = 0;
@@ -380,6 +405,12 @@ DABO_EXPORT void dabo_ofdm(const dabo_mode *m, const cf *in, int nsym, int cfr, 
         for (int n = 0; n < N; n++) { sym[n].re = (float)x[n].re; sym[n].im = (float)x[n].im; }
         if (cfr) {
             const float clip_sq = clip * clip, err_sq = errclip * errclip;
+            double *st = sym_stats ? sym_stats + (size_t)s * DABO_SYM_STATS : NULL;
+            const uint64_t nclip0 = nclip, nerr0 = nerr;
+            if (st) {
+                papr_block(sym, N, &st[0], &st[1]);
+                memcpy(before, sym, sizeof(cf) * N);
+            }
             for (int n = 0; n < N; n++) {
                 const float mag = sym[n].re * sym[n].re + sym[n].im * sym[n].im;
                 if (mag > clip_sq) {
@@ -405,11 +436,22 @@ DABO_EXPORT void dabo_ofdm(const dabo_mode *m, const cf *in, int nsym, int cfr, 
             }
             dft_exec(p, +1, X, x);
             for (int n = 0; n < N; n++) { sym[n].re = (float)x[n].re; sym[n].im = (float)x[n].im; }
+            if (st) {
+                papr_block(sym, N, &st[2], &st[3]);
+                double sum_iq = 0, sum_delta = 0;       /* OfdmGenerator.cpp:262-267 */
+                for (int n = 0; n < N; n++) {
+                    const float dr = sym[n].re - before[n].re, di = sym[n].im - before[n].im;
+                    sum_iq += (double)(before[n].re * before[n].re + before[n].im * before[n].im);
+                    sum_delta += (double)(dr * dr + di * di);
+                }
+                st[4] = sum_iq; st[5] = sum_delta;
+                st[6] = (double)(nclip - nclip0); st[7] = (double)(nerr - nerr0);
+            }
         }
         memcpy(out + (size_t)s * N, sym, sizeof(cf) * N);
     }
     if (cfr_stats) { cfr_stats[0] = nclip; cfr_stats[1] = nerr; }
-    free(X); free(x); free(Xf); free(sym);
+    free(X); free(x); free(Xf); free(sym); free(before);
     dft_plan_free(p);
 }
 
@@ -754,7 +796,81 @@ typedef struct {
     int tii_insert;
     dabo_resampler *rs;
     uint64_t clipped, cfr_clip_count, cfr_err_count;
+    /* CFR read-outs (OfdmGenerator.cpp:186-306): PAPR windows of (L+1)*50 blocks, the last 10 frames'
+     * clip / error-clip ratios and MERs */
+    double *papr_b, *papr_a;          /* [2 * window]: (peak, mean) pairs, oldest first */
+    int papr_nb, papr_na, papr_window;
+    double clip_r[10], err_r[10], mer[10];
+    int n_clip_r, n_err_r, n_mer;
+    int mer_index, papr_clear;
 } dabo_chain;
+
+static void readout_push(double *d, int *n, int cap, double v)
+{
+    if (*n == cap) { memmove(d, d + 1, sizeof(double) * (cap - 1)); (*n)--; }
+    d[(*n)++] = v;
+}
+
+static void papr_push(double *w, int *n, int window, double peak, double mean)
+{
+    if (*n == window) { memmove(w, w + 2, sizeof(double) * 2 * (window - 1)); (*n)--; }
+    w[2 * *n] = peak; w[2 * *n + 1] = mean; (*n)++;
+}
+
+/* PAPRStats::calculate_papr (src/PAPRStats.cpp:72-101) */
+static double papr_calc(const double *w, int n, int window)
+{
+    if (n < window) return 0;
+    double peak = 0, rms2 = 0;
+    for (int i = 0; i < n; i++) {
+        if (w[2 * i] > peak) peak = w[2 * i];
+        rms2 += w[2 * i + 1];
+    }
+    rms2 /= n;
+    return 10.0 * log10(peak / rms2);
+}
+
+/* one frame of per-symbol statistics into the read-outs (OfdmGenerator.cpp:196-306) */
+static void chain_cfr_frame(dabo_chain *h, const double *st, int nsym)
+{
+    const int N = h->m.N;
+    h->mer_index = (h->mer_index + 1) % nsym;
+    if (h->papr_clear) { h->papr_nb = h->papr_na = 0; h->papr_clear = 0; }
+    double nclip = 0, nerr = 0;
+    for (int i = 0; i < nsym; i++) {
+        const double *r = st + (size_t)i * DABO_SYM_STATS;
+        papr_push(h->papr_b, &h->papr_nb, h->papr_window, r[0], r[1]);
+        if (i > 0) papr_push(h->papr_a, &h->papr_na, h->papr_window, r[2], r[3]);
+        if (i > 0 && h->mer_index == i)
+            readout_push(h->mer, &h->n_mer, 10, r[5] > 0 ? 10.0 * log10(r[4] / r[5]) : 90);
+        nclip += r[6]; nerr += r[7];
+    }
+    readout_push(h->clip_r, &h->n_clip_r, 10, nclip / ((double)nsym * N));
+    readout_push(h->err_r, &h->n_err_r, 10, nerr / ((double)nsym * N));
+}
+
+/* OfdmGeneratorCF32::get_parameter "clip_stats" / "papr" (OfdmGenerator.cpp:419-453) */
+DABO_EXPORT int dabo_chain_readout(const dabo_chain *h, const char *name, char *buf, int cap)
+{
+    if (!strcmp(name, "clip_stats")) {
+        if (!h->n_clip_r || !h->n_err_r || !h->n_mer) return snprintf(buf, cap, "No stats available");
+        double a = 0, b = 0, c = 0;
+        for (int i = 0; i < h->n_clip_r; i++) a += h->clip_r[i];
+        for (int i = 0; i < h->n_err_r; i++) b += h->err_r[i];
+        for (int i = 0; i < h->n_mer; i++) c += h->mer[i];
+        return snprintf(buf, cap, "Statistics : %f%% samples clipped, %f%% errors clipped. MER after CFR: %f dB",
+                        a / h->n_clip_r * 100, b / h->n_err_r * 100, c / h->n_mer);
+    }
+    if (!strcmp(name, "papr")) {
+        const double pb = papr_calc(h->papr_b, h->papr_nb, h->papr_window);
+        const double pa = papr_calc(h->papr_a, h->papr_na, h->papr_window);
+        char sb[64], sa[64];
+        if (pb == 0) snprintf(sb, sizeof sb, "N/A"); else snprintf(sb, sizeof sb, "%f", pb);
+        if (pa == 0) snprintf(sa, sizeof sa, "N/A"); else snprintf(sa, sizeof sa, "%f", pa);
+        return snprintf(buf, cap, "PAPR [dB]: %s, %s", sb, sa);
+    }
+    return -1;
+}
 
 DABO_EXPORT dabo_chain *dabo_chain_new(const dabo_cfg *c)
 {
@@ -767,6 +883,9 @@ DABO_EXPORT dabo_chain *dabo_chain_new(const dabo_cfg *c)
     }
     if (c->poly_mode == 1) memcpy(h->poly, c->poly_coefs, sizeof(float) * 10);
     if (c->poly_mode == 2) memcpy(h->poly, c->poly_coefs, sizeof(float) * 33);
+    h->papr_window = (h->m.L + 1) * 50;      /* OfdmGenerator.cpp:59-61 */
+    h->papr_b = calloc((size_t)2 * h->papr_window, sizeof(double));
+    h->papr_a = calloc((size_t)2 * h->papr_window, sizeof(double));
     const uint64_t rate = c->output_rate ? c->output_rate : 2048000;
     /* DabModulator.cpp:154-176 */
     if (c->clock_rate) {
@@ -789,7 +908,7 @@ DABO_EXPORT dabo_chain *dabo_chain_new(const dabo_cfg *c)
 DABO_EXPORT void dabo_chain_free(dabo_chain *h)
 {
     if (!h) return;
-    free(h->fir_taps); free(h->cic); free(h->acp);
+    free(h->fir_taps); free(h->cic); free(h->acp); free(h->papr_b); free(h->papr_a);
     dabo_resampler_free(h->rs);
     free(h);
 }
@@ -847,8 +966,10 @@ DABO_EXPORT long dabo_chain_process(dabo_chain *h, const uint8_t *bits, int stag
     if (stage == 5) { ret = sizeof(cf) * (L + 1) * K; memcpy(out, z, ret); goto done; }
     {
         uint64_t st[2];
-        dabo_ofdm(m, z, L + 1, h->c.cfr_enable, h->c.cfr_clip, h->c.cfr_errclip, x, st);
+        double *ss = h->c.cfr_enable ? calloc((size_t)(L + 1) * DABO_SYM_STATS, sizeof(double)) : NULL;
+        dabo_ofdm_stats(m, z, L + 1, h->c.cfr_enable, h->c.cfr_clip, h->c.cfr_errclip, x, st, ss);
         h->cfr_clip_count = st[0]; h->cfr_err_count = st[1];
+        if (ss) { chain_cfr_frame(h, ss, L + 1); free(ss); }
     }
     if (stage == 6) { ret = sizeof(cf) * (L + 1) * N; memcpy(out, x, ret); goto done; }
     dabo_gain(m, x, L + 1, h->c.gain_mode, h->c.digital_gain, h->c.normalise, h->c.gain_variance, y);

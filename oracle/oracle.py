@@ -196,6 +196,15 @@ class OracleChain:
     def clipped(self):
         return lib().dabo_chain_clipped(self._h)
 
+    def get_param(self, name):
+        """The CFR read-outs "clip_stats" / "papr" (OfdmGenerator.cpp:419-453)."""
+        buf = ctypes.create_string_buffer(256)
+        L = lib()
+        L.dabo_chain_readout.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+        if L.dabo_chain_readout(self._h, name.encode(), buf, 256) < 0:
+            raise KeyError(name)
+        return buf.value.decode()
+
     def close(self):
         if self._h:
             lib().dabo_chain_free(self._h)

@@ -116,6 +116,7 @@ struct Harness {
     Buffer out;
     std::shared_ptr<BitsInput> input;
     std::unique_ptr<Flowgraph> fg;
+    std::shared_ptr<OfdmGeneratorCF32> ofdm;
     std::string err;
 };
 
@@ -224,6 +225,7 @@ void *ref_create(const ref_cfg *c)
 
         auto cifOfdm = make_shared<OfdmGeneratorCF32>(1 + m.L, m.K, m.N,
                 s.enableCfr, s.cfrClip, s.cfrErrorClip);
+        h->ofdm = cifOfdm;
         auto cifGain = make_shared<GainControl>(m.N, s.gainMode, s.digitalgain,
                 s.normalise, s.gainmodeVariance);
         auto cifGuard = make_shared<GuardIntervalInserter>(m.L, m.N,
@@ -282,6 +284,23 @@ void *ref_create(const ref_cfg *c)
     catch (const std::exception &e) {
         g_err = e.what();
         return nullptr;
+    }
+}
+
+/* OfdmGeneratorCF32::get_parameter ("clip_stats", "papr", "cfr", ...) of the chain's generator */
+int ref_ofdm_get_parameter(void *hp, const char *name, char *buf, size_t cap)
+{
+    auto h = static_cast<Harness*>(hp);
+    try {
+        if (!h->ofdm) throw std::runtime_error("chain stops before the OfdmGenerator");
+        const std::string v = h->ofdm->get_parameter(name);
+        if (v.size() + 1 > cap) throw std::runtime_error("buffer too small");
+        memcpy(buf, v.c_str(), v.size() + 1);
+        return 0;
+    }
+    catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
     }
 }
 

@@ -63,6 +63,7 @@ def lib():
                                      ctypes.c_void_p, ctypes.c_size_t]
         _lib.ref_destroy.argtypes = [ctypes.c_void_p]
         _lib.ref_last_error.restype = ctypes.c_char_p
+        _lib.ref_ofdm_get_parameter.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     return _lib
 
 
@@ -137,6 +138,13 @@ class RefChain:
             else:
                 assert o.size == 0
         return outs
+
+    def get_param(self, name):
+        """OfdmGeneratorCF32::get_parameter of this chain ("clip_stats", "papr", ...)."""
+        buf = ctypes.create_string_buffer(512)
+        if lib().ref_ofdm_get_parameter(self._h, name.encode(), buf, 512) != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return buf.value.decode()
 
     def close(self):
         if self._h:

@@ -38,3 +38,12 @@ def slices(o):
         v = o.astype(np.float64)
         chk = np.array([v[0::2].sum(), v[1::2].sum(), (v ** 2).sum()])
     return o[:HEAD].copy(), o[-HEAD:].copy(), o[HEAD:-HEAD:STRIDE].copy(), chk
+
+
+# CFR read-outs ("clip_stats", "papr"): strings of the reference after `after` frames of the seeded stream
+# (tests/golden/make_cfr_readouts.py -> cfr_readouts.json).  The PAPR windows fill after 50 frames.
+READOUT_CASES = {
+    "tm2_cfr_errclip": dict(seed=201, n_tf=56, after=[1, 9, 50, 51, 56], cfg=dict(mode=2, cfr=(40.0, 0.02))),
+    "tm1_cfr_tii": dict(seed=202, n_tf=52, after=[3, 52], cfg=dict(mode=1, cfr=(80.0, 0.01), tii=(3, 5, 0))),
+    "tm3_cfr_noerr": dict(seed=203, n_tf=12, after=[12], cfg=dict(mode=3, cfr=(30.0, 0.5), gain_mode="max")),
+}

@@ -78,3 +78,76 @@ def test_cuda_matches_golden(name):
             pytest.skip("not implemented on the GPU yet: %s" % e)
         raise
     check(name, list(mod.process_batch(bits)))
+
+
+# ---------------------------------------------------------------------------
+# CFR read-outs: the reference's "clip_stats" / "papr" strings (OfdmGenerator.cpp:419-453)
+# ---------------------------------------------------------------------------
+import json
+import re
+
+from golden_cases import READOUT_CASES
+
+
+def readout_numbers(s):
+    """The numbers of a read-out string; 'N/A' (PAPR window not full yet) -> None."""
+    return [None if t == "N/A" else float(t) for t in re.findall(r"N/A|-?\d+\.\d+", s)]
+
+
+def check_readouts(name, get_param, feed, tol_pct, tol_db):
+    with open(os.path.join(GOLDEN, "cfr_readouts.json")) as f:
+        want = json.load(f)[name]
+    case = READOUT_CASES[name]
+    rng = np.random.default_rng(case["seed"])
+    bits = rng.integers(0, 256, (case["n_tf"], oracle.mode_params(case["cfg"]["mode"]).tf_bytes), dtype=np.uint8)
+    done = 0
+    for n in case["after"]:
+        feed(bits[done:n])
+        done = n
+        for key, tols in (("clip_stats", (tol_pct, tol_pct, tol_db)), ("papr", (tol_db, tol_db))):
+            got, ref = get_param(key), want[str(n)][key]
+            assert re.sub(r"-?\d+\.\d+", "#", got) == re.sub(r"-?\d+\.\d+", "#", ref), (n, got, ref)
+            for g, r, tol in zip(readout_numbers(got), readout_numbers(ref), tols):
+                if r is not None:
+                    assert abs(g - r) <= tol * max(1.0, abs(r)), (n, key, got, ref)
+
+
+@pytest.mark.parametrize("name", sorted(READOUT_CASES))
+def test_oracle_readouts_match_golden(name):
+    ora = oracle.OracleChain(**READOUT_CASES[name]["cfg"])
+    check_readouts(name, ora.get_param, lambda b: ora.run(b), 1e-4, 1e-4)   # a bin at the clip threshold may flip
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(READOUT_CASES))
+@pytest.mark.parametrize("api", ["batch", "single", "device"])
+def test_cuda_readouts_match_golden(name, api):
+    """The symbol kernel's per-symbol CFR records, aggregated on the host like OfdmGenerator.cpp:196-306.
+    Tolerances: a sample or error bin within rounding of the clip threshold may fall on the other side
+    (2e-3 relative on the ratios); MER comes from frequency-domain sums (Parseval) in float32: 0.01 dB."""
+    dm = dabmod_loader.load()
+    mod = dm.Modulator(max_batch=16, **READOUT_CASES[name]["cfg"])
+
+    def feed(b):
+        if api == "single":
+            for x in b:
+                mod.process(x)
+        elif api == "batch":
+            for i in range(0, len(b), 16):
+                mod.process_batch(b[i:i + 16])
+        else:
+            import torch
+            for i in range(0, len(b), 16):
+                part = b[i:i + 16]
+                d_in = torch.from_numpy(np.ascontiguousarray(part)).cuda()
+                d_out = torch.empty(len(part) * mod.tf_out_bytes, dtype=torch.uint8, device="cuda")
+                mod.process_batch_device(d_in.data_ptr(), len(part), d_out.data_ptr())
+                mod.synchronize()
+
+    check_readouts(name, mod.get_param, feed, 2e-3, 1e-2)
+    with pytest.raises(dm.DabModError):
+        mod.set_param("papr", "1")
+    # changing a CFR parameter restarts the PAPR windows (OfdmGenerator.cpp:384-395)
+    mod.set_param("clip", "70")
+    mod.process(np.zeros(mod.tf_in_bytes, np.uint8))
+    assert mod.get_param("papr") == "PAPR [dB]: N/A, N/A"
