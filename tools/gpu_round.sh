@@ -15,3 +15,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_symbols -s 2 -
 ncu --set full --clock-control none --import-source on -k regex:k_fir -s 2 -c 1 -f -o gpurun_out/prof_fir_$TAG python bench.py --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/ncu_fir.log 2>&1
 ls -la gpurun_out | tail -8
 fi
+if [ "${NCU:-1}" = "1" ]; then
+bash tools/prof_kernel.sh k_resample_q c5 resq_$TAG
+bash tools/prof_kernel.sh k_resample_up "c3 " resup_$TAG
+fi
