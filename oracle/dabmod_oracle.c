@@ -782,7 +782,13 @@ typedef struct {
     int32_t  poly_mode;       /* 0 none, 1 odd polynomial (10 coefs), 2 LUT (scale + 32) */
     const float *poly_coefs;
     int32_t  format;          /* 0 complexf, 1 s16, 2 u8, 3 s8 */
+    int32_t  fixed_point;     /* 1 = FFTEngine::KISS: fixed_oracle.c after the multiplexer, int16 I/Q out */
 } dabo_cfg;
+
+/* fixed_oracle.c */
+void dabo_fix_carriers(const float *z, long n_floats, int16_t *out);
+void dabo_ofdm_fixed(int N, int K, const int16_t *in, int nsym, int16_t *out);
+void dabo_guard_fixed(int N, int L, int null_size, int sym_size, const int16_t *in, int W, int16_t *out);
 
 typedef struct {
     dabo_cfg c;
@@ -954,6 +960,24 @@ DABO_EXPORT long dabo_chain_process(dabo_chain *h, const uint8_t *bits, int stag
         if (h->c.tii_enable && h->tii_insert)
             dabo_tii_symbol(m, h->acp, h->c.tii_old_variant, ref, z);
         h->tii_insert = !h->tii_insert;
+    }
+    if (h->c.fixed_point) {
+        /* DabModulator.cpp:144-224 with fftEngine == KISS: complexfix carriers, OfdmGeneratorFixed, no
+         * GainControl, GuardIntervalInserter<complexfix>; the output is already s16 */
+        int16_t *zi = malloc(sizeof(int16_t) * 2 * (size_t)(L + 1) * K);
+        int16_t *xi = malloc(sizeof(int16_t) * 2 * (size_t)(L + 1) * N);
+        dabo_fix_carriers((const float *)z, 2L * (L + 1) * K, zi);
+        if (stage >= 1 && stage <= 4) { ret = 4L * (L + 1) * K; memcpy(out, zi, ret); }
+        else {
+            dabo_ofdm_fixed(N, K, zi, L + 1, xi);
+            if (stage == 6) { ret = 4L * (L + 1) * N; memcpy(out, xi, ret); }
+            else {
+                dabo_guard_fixed(N, L, m->null_size, m->sym_size, xi, h->c.window_overlap, out);
+                ret = 4L * m->tf_samples;
+            }
+        }
+        free(zi); free(xi);
+        goto done;
     }
     if (stage == 4) { ret = sizeof(cf) * (L + 1) * K; memcpy(out, z, ret); goto done; }
     if (h->use_cic) {

@@ -46,12 +46,13 @@ class Cfg(ctypes.Structure):
         ("poly_mode", ctypes.c_int32),
         ("poly_coefs", ctypes.POINTER(ctypes.c_float)),
         ("format", ctypes.c_int32),
+        ("fixed_point", ctypes.c_int32),
     ]
 
 
 def build():
     """Compile liboracle.so (gcc, ~1 s). Building the checker is not using it."""
-    srcs = [os.path.join(HERE, f) for f in ("dabmod_oracle.c", "coder_oracle.c")]
+    srcs = [os.path.join(HERE, f) for f in ("dabmod_oracle.c", "coder_oracle.c", "fixed_oracle.c")]
     if (not os.path.exists(LIB)) or any(os.path.getmtime(LIB) < os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     return LIB
@@ -137,8 +138,9 @@ class OracleChain:
 
     def __init__(self, mode=1, gain_mode="var", output_rate=2048000, clock_rate=0,
                  digital_gain=1.0, normalise=1.0, gain_variance=4.0, window_overlap=0,
-                 cfr=None, tii=None, fir_taps=None, poly=None, lut=None, fmt=None):
+                 cfr=None, tii=None, fir_taps=None, poly=None, lut=None, fmt=None, fixed_point=False):
         c = Cfg()
+        c.fixed_point = 1 if fixed_point else 0
         c.mode = mode
         c.gain_mode = GAIN_MODES[gain_mode]
         c.output_rate = output_rate
@@ -186,7 +188,7 @@ class OracleChain:
         n = lib().dabo_chain_process(self._h, bits.ctypes.data, st, self._buf.ctypes.data)
         if n < 0:
             raise RuntimeError("dabo_chain_process failed")
-        dt = FORMAT_DTYPE[self.cfg.format] if st == 0 else np.complex64
+        dt = np.int16 if self.cfg.fixed_point else FORMAT_DTYPE[self.cfg.format] if st == 0 else np.complex64
         return self._buf[:n].copy().view(dt)
 
     def run(self, bits_tfs, stage="final"):

@@ -76,6 +76,9 @@ struct ref_cfg {
      * intermediate buffers can be compared: qpsk, freq, diff, mux, ciceq,
      * ofdm, gain, guard, fir, resampler, poly, format, NULL/"" = all. */
     const char *stop_after;
+    /* 1 = FFTEngine::KISS: the fixed-point chain of DabModulator.cpp:144-224 (complexfix carriers,
+     * OfdmGeneratorFixed, no GainControl; FIR / resampler / predistortion are rejected there) */
+    int32_t  fixed_point;
 };
 
 } // extern "C"
@@ -159,7 +162,14 @@ void *ref_create(const ref_cfg *c)
         h->m = mode_params(c->mode);
         const Mode &m = h->m;
         const unsigned mode = c->mode;
-        const bool fixedPoint = false;
+        const bool fixedPoint = c->fixed_point != 0;
+        if (fixedPoint) {
+            /* DabModulator.cpp:249,257,265: "fixed point doesn't support ..." */
+            if (!s.filterTapsFilename.empty()) throw std::runtime_error("fixed point doesn't support fir filter");
+            if (!s.polyCoefFilename.empty()) throw std::runtime_error("fixed point doesn't support predistortion");
+            if (s.outputRate != 2048000) throw std::runtime_error("fixed point doesn't support resampler");
+            s.fftEngine = FFTEngine::KISS;
+        }
 
         h->fg = make_unique<Flowgraph>(false);
         Flowgraph &fg = *h->fg;
@@ -189,7 +199,7 @@ void *ref_create(const ref_cfg *c)
             fg.connect(cifDiff, output);
             return h.release();
         }
-        auto cifNull = make_shared<NullSymbol>(m.K, sizeof(complexf));
+        auto cifNull = make_shared<NullSymbol>(m.K, fixedPoint ? sizeof(complexfix) : sizeof(complexf));
         auto cifSig = make_shared<SignalMultiplexer>();
 
         /* DabModulator.cpp:154-176 */
@@ -223,11 +233,19 @@ void *ref_create(const ref_cfg *c)
             tii.reset();
         }
 
-        auto cifOfdm = make_shared<OfdmGeneratorCF32>(1 + m.L, m.K, m.N,
-                s.enableCfr, s.cfrClip, s.cfrErrorClip);
-        h->ofdm = cifOfdm;
-        auto cifGain = make_shared<GainControl>(m.N, s.gainMode, s.digitalgain,
-                s.normalise, s.gainmodeVariance);
+        shared_ptr<ModPlugin> cifOfdm;
+        shared_ptr<GainControl> cifGain;
+        if (fixedPoint) {
+            cifOfdm = make_shared<OfdmGeneratorFixed>(1 + m.L, m.K, m.N);     /* DabModulator.cpp:208-213 */
+        }
+        else {
+            auto ofdm = make_shared<OfdmGeneratorCF32>(1 + m.L, m.K, m.N,
+                    s.enableCfr, s.cfrClip, s.cfrErrorClip);
+            h->ofdm = ofdm;
+            cifOfdm = ofdm;
+            cifGain = make_shared<GainControl>(m.N, s.gainMode, s.digitalgain,
+                    s.normalise, s.gainmodeVariance);
+        }
         auto cifGuard = make_shared<GuardIntervalInserter>(m.L, m.N,
                 m.nullSize, m.symSize, s.ofdmWindowOverlap, s.fftEngine);
 

@@ -40,6 +40,7 @@ class _RefCfg(ctypes.Structure):
         ("poly_coef_file", ctypes.c_char_p),
         ("format", ctypes.c_char_p),
         ("stop_after", ctypes.c_char_p),
+        ("fixed_point", ctypes.c_int32),
     ]
 
 
@@ -76,7 +77,7 @@ class RefChain:
     def __init__(self, mode=1, gain_mode="var", output_rate=2048000, clock_rate=0,
                  digital_gain=1.0, normalise=1.0, gain_variance=4.0, window_overlap=0,
                  cfr=None, tii=None, fir_taps_file=None, poly_coef_file=None,
-                 poly_threads=1, fmt=None, stop_after=None):
+                 poly_threads=1, fmt=None, stop_after=None, fixed_point=False):
         c = _RefCfg()
         c.mode = mode
         c.gain_mode = GAIN_MODES[gain_mode]
@@ -100,6 +101,7 @@ class RefChain:
         c.poly_coef_file = enc(poly_coef_file)
         c.format = enc(fmt)
         c.stop_after = enc(stop_after)
+        c.fixed_point = 1 if fixed_point else 0
         self._cfg = c
         self.mode = mode
         self._h = lib().ref_create(ctypes.byref(c))

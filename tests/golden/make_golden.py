@@ -30,7 +30,10 @@ from golden_cases import CASES, HEAD, STRIDE, slices   # noqa: E402
 
 def main():
     tmp = tempfile.mkdtemp()
+    only = sys.argv[1] if len(sys.argv) > 1 else ""      # optional name prefix: regenerate a subset
     for name, case in CASES.items():
+        if not name.startswith(only):
+            continue
         kw = dict(case["cfg"])
         rng = np.random.default_rng(case["seed"])
         bits = rng.integers(0, 256, (case["n_tf"], refwrap.TF_BYTES[kw["mode"]]), dtype=np.uint8)
@@ -44,6 +47,8 @@ def main():
             ref_kw["poly_coef_file"] = p
             ref_kw["poly_threads"] = 1
         dt = {None: np.complex64, "s16": np.int16, "u8": np.uint8, "s8": np.int8}[kw.get("fmt")]
+        if kw.get("fixed_point"):
+            dt = np.int16
         outs = refwrap.RefChain(**ref_kw).run(bits, dtype=dt)
         arrs = {"bits": bits}
         for i, o in enumerate(outs):

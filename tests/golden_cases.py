@@ -25,6 +25,12 @@ CASES = {
     "tm1_cfr": dict(seed=112, n_tf=2, cfg=dict(mode=1, cfr=(50.0, 0.1))),
     "tm1_ciceq": dict(seed=113, n_tf=1, cfg=dict(mode=1, clock_rate=32768000)),
     "tm2_res_down_1536": dict(seed=114, n_tf=3, cfg=dict(mode=2, fir=True, output_rate=1536000)),
+    # row N4: the fixed-point engine (FFTEngine::KISS), int16 I/Q, bit-exact
+    "fix_tm1": dict(seed=301, n_tf=2, cfg=dict(mode=1, fixed_point=True)),
+    "fix_tm2_tii": dict(seed=302, n_tf=3, cfg=dict(mode=2, fixed_point=True, tii=(4, 17, 0))),
+    "fix_tm3_window": dict(seed=303, n_tf=2, cfg=dict(mode=3, fixed_point=True, window_overlap=12)),
+    "fix_tm4": dict(seed=304, n_tf=2, cfg=dict(mode=4, fixed_point=True)),
+    "fix_tm1_window_tii": dict(seed=305, n_tf=2, cfg=dict(mode=1, fixed_point=True, window_overlap=40, tii=(23, 69, 1))),
 }
 
 

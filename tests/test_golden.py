@@ -36,9 +36,15 @@ def check(name, outs):
     g = load(name)
     case = CASES[name]
     integer = case["cfg"].get("fmt") is not None
+    exact = bool(case["cfg"].get("fixed_point"))      # integer arithmetic end to end: bit for bit
     for i, o in enumerate(outs):
         assert o.size == int(g["size%d" % i][0])
         h, t, s, chk = slices(o)
+        if exact:
+            for part, got in (("head", h), ("tail", t), ("stride", s)):
+                assert np.array_equal(got, g["%s%d" % (part, i)]), (name, i, part)
+            assert np.array_equal(chk, g["chk%d" % i]), (name, i)
+            continue
         for part, got in (("head", h), ("tail", t), ("stride", s)):
             want = g["%s%d" % (part, i)]
             if integer:

@@ -183,3 +183,29 @@ def test_full_chain_c3(rng, tmp_path):
     ora = oracle.OracleChain(fir_taps=oracle.fir_default_taps(), poly=am + pm, **kw).run(bits)
     for r, o in zip(ref, ora):
         assert rel_rms(o, r) < FFT_TOL
+
+
+# ---------------------------------------------------------------------------
+# Row N4: the fixed-point engine (FFTEngine::KISS, DabModulator.cpp:144-224) -- integer arithmetic, bit-exact
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("kw", [dict(), dict(window_overlap=16), dict(window_overlap=5, tii=(2, 9, 0)),
+                                dict(tii=(11, 40, 1))], ids=["plain", "window", "window_tii", "tii_old"])
+def test_fixed_point_chain_bit_exact(rng, mode, kw):
+    """complexfix carriers (fpm rounding multiply), KISS FIXED_POINT=16 inverse FFT with its per-stage scaling,
+    GuardIntervalInserter<complexfix> with the fixed-point window: oracle/fixed_oracle.c == reference, every bit."""
+    if mode > 2 and "tii" in kw:
+        kw = {k: v for k, v in kw.items() if k != "tii"}          # TIIError -> NullSymbol (DabModulator.cpp:180-190)
+    bits = bits_for(rng, mode, 3)
+    for stage in ("mux", "ofdm", None):
+        ref = refwrap.RefChain(mode=mode, fixed_point=True, stop_after=stage, **kw).run(bits, dtype=np.int16)
+        ora = oracle.OracleChain(mode=mode, fixed_point=True, **kw).run(bits, stage=stage or "final")
+        for r, o in zip(ref, ora):
+            assert r.size == o.size and np.array_equal(r, o), stage
+
+
+def test_fixed_point_rejects_float_only_blocks():
+    """DabModulator.cpp:249,257,265"""
+    for kw in (dict(fir_taps_file="default"), dict(output_rate=4096000)):
+        with pytest.raises(RuntimeError, match="fixed point doesn't support"):
+            refwrap.RefChain(mode=1, fixed_point=True, **kw)
