@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DABMOD_B200_ABI_VERSION 1
+#define DABMOD_B200_ABI_VERSION 2
 
 enum {
     DABMOD_B200_OK = 0,
@@ -48,6 +48,13 @@ enum { DABMOD_B200_GAIN_FIX = 0, DABMOD_B200_GAIN_MAX = 1, DABMOD_B200_GAIN_VAR 
 /* Output sample format, reference src/FormatConverter.cpp:112-165 and
  * DabMod.cpp:250-363 ("complexf" = no FormatConverter node). */
 enum { DABMOD_B200_FMT_COMPLEXF = 0, DABMOD_B200_FMT_S16 = 1, DABMOD_B200_FMT_U8 = 2, DABMOD_B200_FMT_S8 = 3 };
+
+/* FFTEngine, reference src/ConfigParser.h:39-43.  FFTW = the float32 chain; KISS = the fixed-point chain of
+ * DabModulator.cpp:144-224: complexfix carriers, OfdmGeneratorFixed (vendored KISS FFT, FIXED_POINT=16), no
+ * GainControl, GuardIntervalInserter<complexfix>; the output is int16 I/Q ("KISS is already in s16",
+ * DabModulator.cpp:279) and bit-exact with the reference.  Like the reference it rejects FIR, resampler and
+ * predistortion ("fixed point doesn't support ...", DabModulator.cpp:249,257,265); CFR does not exist there. */
+enum { DABMOD_B200_FFT_FLOAT = 0, DABMOD_B200_FFT_KISS_FIXED = 1 };
 
 /* MemlessPoly, reference src/MemlessPoly.cpp:109-110,145-229 */
 enum { DABMOD_B200_DPD_NONE = 0, DABMOD_B200_DPD_ODD_POLY = 1, DABMOD_B200_DPD_LUT = 2 };
@@ -79,6 +86,7 @@ typedef struct dabmod_b200_config {
     const float *dpd_coefs;   /* ODD_POLY: am0..4, pm0..4 (10 floats); LUT: scalefactor + 32 entries (33 floats) */
     int32_t  format;          /* DABMOD_B200_FMT_* */
     int32_t  max_batch;       /* largest n_tf a *_batch call will pass (sizes device buffers), default 1 */
+    int32_t  fft_engine;      /* DABMOD_B200_FFT_*, default FLOAT (fftEngine = FFTW) */
 } dabmod_b200_config;
 
 typedef struct dabmod_b200 dabmod_b200;
@@ -96,7 +104,7 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out);
 void dabmod_b200_destroy(dabmod_b200 *h);
 
 /* Bytes per TF on either side of the path. in: (L-1)*K/4 (BlockPartitioner);
- * out: samples * {8,4,2,2}. */
+ * out: samples * {8,4,2,2}; the fixed-point engine always writes int16 pairs (4 bytes per sample). */
 size_t dabmod_b200_tf_in_bytes(const dabmod_b200 *h);
 size_t dabmod_b200_tf_out_bytes(const dabmod_b200 *h);
 size_t dabmod_b200_tf_out_samples(const dabmod_b200 *h);

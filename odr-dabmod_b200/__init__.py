@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libdabmod_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 GAIN_MODES = {"fix": 0, "max": 1, "var": 2}
 FORMATS = {None: 0, "": 0, "complexf": 0, "s16": 1, "u8": 2, "s8": 3}
 FORMAT_DTYPE = {0: np.complex64, 1: np.int16, 2: np.uint8, 3: np.int8}
@@ -68,6 +68,7 @@ class Config(ctypes.Structure):
         ("dpd_coefs", ctypes.POINTER(ctypes.c_float)),
         ("format", ctypes.c_int32),
         ("max_batch", ctypes.c_int32),
+        ("fft_engine", ctypes.c_int32),
     ]
 
 
@@ -221,10 +222,11 @@ class Modulator:
     def __init__(self, mode=1, gain_mode="var", output_rate=2048000, clock_rate=0,
                  digital_gain=1.0, normalise=1.0, gain_variance=4.0, window_overlap=0,
                  cfr=None, tii=None, fir_taps=None, poly=None, lut=None, fmt=None,
-                 max_batch=1, device=0):
+                 max_batch=1, device=0, fixed_point=False):
         L = lib()
         c = Config()
         L.dabmod_b200_config_init(ctypes.byref(c))
+        c.fft_engine = 1 if fixed_point else 0
         c.device = device
         c.mode = mode
         c.gain_mode = GAIN_MODES[gain_mode]
@@ -265,7 +267,7 @@ class Modulator:
         self.tf_in_bytes = L.dabmod_b200_tf_in_bytes(self._h)
         self.tf_out_bytes = L.dabmod_b200_tf_out_bytes(self._h)
         self.tf_out_samples = L.dabmod_b200_tf_out_samples(self._h)
-        self.out_dtype = FORMAT_DTYPE[c.format]
+        self.out_dtype = np.int16 if fixed_point else FORMAT_DTYPE[c.format]
         self.max_batch = max_batch
 
     # -- host buffers -------------------------------------------------------

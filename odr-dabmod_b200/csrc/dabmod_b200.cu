@@ -20,6 +20,7 @@
 #include "resample.cuh"
 #include "resample_up.cuh"
 #include "resample_q.cuh"
+#include "symbols_fixed.cuh"
 #include "symbols_warp.cuh"
 #include "tables.h"
 
@@ -207,6 +208,12 @@ struct dabmod_b200 {
     DevBuf<unsigned long long> d_clipped;
     int tii_count = 0;
 
+    // fixed-point engine (symbols_fixed.cuh)
+    DevBuf<uint16_t> d_fx_pos_of_src, d_fx_tii_pos;
+    DevBuf<short2> d_fx_tw, d_fx_tii_val;
+    DevBuf<short> d_fx_window;
+    std::vector<int> fx_p, fx_m;   // kf_factor's (radix, remaining size) list
+
     // work buffers for max_batch TFs
     DevBuf<uint8_t> d_bits;
     DevBuf<unsigned char> d_out;
@@ -257,7 +264,8 @@ struct dabmod_b200 {
     {
         return has_res ? (size_t)m.tf_samples * rp.L / rp.M : (size_t)m.tf_samples;
     }
-    size_t out_bytes_per_tf() const { return out_samples_per_tf() * format_bytes(cfg.format); }
+    bool fixed() const { return cfg.fft_engine == DABMOD_B200_FFT_KISS_FIXED; }
+    size_t out_bytes_per_tf() const { return out_samples_per_tf() * (fixed() ? 4 : format_bytes(cfg.format)); }
     bool has_fir() const { return !fir_taps.empty(); }
     bool has_post() const { return dpd_mode != 0 || cfg.format != DABMOD_B200_FMT_COMPLEXF; }
 };
@@ -320,6 +328,69 @@ void build_tables(dabmod_b200 *h)
     if (h->dpd_mode == DABMOD_B200_DPD_LUT) {
         std::vector<float> lut(h->dpd + 1, h->dpd + 33);
         h->d_lut.upload(lut, s);
+    }
+    if (h->fixed()) {
+        // KISS plan of the mode's transform (kiss_fft.c:293-315 kf_factor, :325-355 kiss_fft_alloc)
+        const int N = m.N;
+        h->fx_p.clear(); h->fx_m.clear();
+        {
+            int p = 4, rem = N;
+            const double floor_sqrt = std::floor(std::sqrt((double)N));
+            do {
+                while (rem % p) {
+                    switch (p) {
+                        case 4: p = 2; break;
+                        case 2: p = 3; break;
+                        default: p += 2; break;
+                    }
+                    if (p > floor_sqrt) p = rem;
+                }
+                rem /= p;
+                h->fx_p.push_back(p);
+                h->fx_m.push_back(rem);
+            } while (rem > 1);
+        }
+        for (int p : h->fx_p)
+            if (p != 2 && p != 4) throw ApiError(DABMOD_B200_EUNSUPPORTED, "fixed-point FFT: radix other than 2 and 4");
+        if ((int)h->fx_p.size() > FX_MAX_STAGES) throw ApiError(DABMOD_B200_EUNSUPPORTED, "fixed-point FFT: too many stages");
+        std::vector<short2> tw(N);
+        for (int i = 0; i < N; i++) {
+            const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
+            const double phase = 2 * pi * i / N;          // inverse transform: -(-2 pi i / N)
+            tw[i] = make_short2((short)std::floor(.5 + 32767 * std::cos(phase)),
+                                (short)std::floor(.5 + 32767 * std::sin(phase)));
+        }
+        h->d_fx_tw.upload(tw, s);
+        // kf_work reads the input in mixed-radix digit-reversed order: position -> input index
+        std::vector<int> idx_of_pos(N), pos_of_idx(N);
+        std::function<void(int, int, int, size_t)> fill = [&](int pos0, int idx0, int fstride, size_t level) {
+            const int p = h->fx_p[level], mm = h->fx_m[level];
+            for (int q = 0; q < p; q++) {
+                if (mm == 1) idx_of_pos[pos0 + q] = idx0 + q * fstride;
+                else fill(pos0 + q * mm, idx0 + q * fstride, fstride * p, level + 1);
+            }
+        };
+        fill(0, 0, 1, 0);
+        for (int i = 0; i < N; i++) pos_of_idx[idx_of_pos[i]] = i;
+        std::vector<uint16_t> pos_src(m.K);
+        for (int j = 0; j < m.K; j++) pos_src[j] = (uint16_t)pos_of_idx[bin[j]];
+        h->d_fx_pos_of_src.upload(pos_src, s);
+        std::vector<uint16_t> tpos;
+        std::vector<short2> tv;
+        for (size_t i = 0; i < tbin.size(); i++) {
+            tpos.push_back((uint16_t)pos_of_idx[tbin[i]]);
+            // PhaseReference.cpp:139-150: fixed_16{1} = 16384
+            tv.push_back(make_short2((short)(tval[2 * i] * 16384.0f), (short)(tval[2 * i + 1] * 16384.0f)));
+        }
+        h->d_fx_tii_pos.upload(tpos, s);
+        h->d_fx_tii_val.upload(tv, s);
+        if (c.window_overlap > 0) {
+            // GuardIntervalInserter.cpp:103-112: windowFix[i] = fixed((double)(float)value), rounded
+            const std::vector<float> wf = guard_window(c.window_overlap);
+            std::vector<short> wi(wf.size());
+            for (size_t i = 0; i < wf.size(); i++) wi[i] = (short)((double)wf[i] * 16384.0 + 0.5);
+            h->d_fx_window.upload(wi, s);
+        }
     }
     h->tables_dirty = false;
 }
@@ -621,11 +692,59 @@ void enqueue_resampler(dabmod_b200 *h, const float2 *in, size_t n_tf, void *d_ou
     CUDA_CHECK(cudaMemcpyAsync(h->d_hist.p, in + total - rp.ni, sizeof(float2) * rp.ni, cudaMemcpyDeviceToDevice, s));
 }
 
+// Fixed-point engine: one kernel, bits -> int16 I/Q (symbols_fixed.cuh)
+void enqueue_fixed(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst, uint64_t stream_tf, cudaStream_t s,
+                   uint32_t &launches)
+{
+    const ModeInfo &m = h->m;
+    const dabmod_b200_config &c = h->cfg;
+    FixParams fp{};
+    fp.L = m.L; fp.K = m.K; fp.N = m.N;
+    fp.null_size = m.null_size; fp.sym_size = m.sym_size;
+    fp.tf_in_bytes = m.tf_in_bytes; fp.tf_samples = m.tf_samples;
+    fp.G = FX_POINTS / m.N;
+    fp.n_groups = (m.L + 1 + fp.G - 1) / fp.G;
+    {
+        // as in k_symbols: enough CTAs to fill the machine a few times, chunks long enough to amortise the
+        // tables and the phase prefix; with windowing a TF is one chunk (the falling edges chain through it)
+        const int target_ctas = h->sm_count * 8 * 2;
+        int chunks = (int)std::min<size_t>((size_t)fp.n_groups / 2, std::max<size_t>(1, (target_ctas + n_tf - 1) / n_tf));
+        chunks = std::max(1, std::min(chunks, 11));
+        if (h->force_chunks > 0) chunks = std::max(1, std::min(h->force_chunks, fp.n_groups / 2));
+        if (c.window_overlap > 0) chunks = 1;
+        fp.groups_per_chunk = (fp.n_groups + chunks - 1) / chunks;
+        fp.n_chunks = (fp.n_groups + fp.groups_per_chunk - 1) / fp.groups_per_chunk;
+    }
+    fp.pos_of_src = h->d_fx_pos_of_src.p;
+    fp.phase0 = h->d_phase0.p;
+    fp.tw = h->d_fx_tw.p;
+    fp.n_stages = (int)h->fx_p.size();
+    for (int i = 0; i < fp.n_stages; i++) { fp.stage_p[i] = h->fx_p[i]; fp.stage_m[i] = h->fx_m[i]; }
+    fp.tii_count = h->tii_count;
+    fp.tii_parity = 0;
+    fp.tii_pos = h->d_fx_tii_pos.p;
+    fp.tii_val = h->d_fx_tii_val.p;
+    fp.window = c.window_overlap;
+    fp.window_tab = h->d_fx_window.p;
+    fp.bits = d_bits;
+    fp.out = reinterpret_cast<short2 *>(dst);
+    fp.tf_offset = stream_tf;
+    ProfScope prof(h, "k_symbols_fix", s);
+    k_symbols_fix<<<(unsigned)(n_tf * fp.n_chunks), FX_THREADS, 0, s>>>(fp);
+    CUDA_CHECK(cudaGetLastError());
+    prof.end();
+    launches++;
+}
+
 // Enqueue the kernel family for n_tf TFs: d_bits -> d_out.  `tmp_tf0` = index of
 // the first TF within the handle's work buffers (for the temp buffer offsets).
 void enqueue(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_out, size_t tmp_tf0,
              uint64_t stream_tf, cudaStream_t s, uint32_t &launches)
 {
+    if (h->fixed()) {
+        enqueue_fixed(h, d_bits, n_tf, d_out, stream_tf, s, launches);
+        return;
+    }
     if (!h->has_res) {
         enqueue_front(h, d_bits, n_tf, d_out, true, tmp_tf0, stream_tf, s, launches);
         return;
@@ -662,6 +781,23 @@ void validate_config(const dabmod_b200_config &c)
     format_bytes(c.format);
     check_window(c.mode, c.window_overlap);
     if (c.max_batch < 0) throw ApiError(DABMOD_B200_EINVAL, "max_batch < 0");
+    if (c.fft_engine != DABMOD_B200_FFT_FLOAT && c.fft_engine != DABMOD_B200_FFT_KISS_FIXED)
+        throw ApiError(DABMOD_B200_EINVAL, "unknown fft_engine");
+    if (c.fft_engine == DABMOD_B200_FFT_KISS_FIXED) {
+        // DabModulator.cpp:249,257,265
+        if (c.fir_ntaps > 0) throw ApiError(DABMOD_B200_EINVAL, "fixed point doesn't support fir filter");
+        if (c.dpd_mode != 0) throw ApiError(DABMOD_B200_EINVAL, "fixed point doesn't support predistortion");
+        if (c.output_rate != 0 && c.output_rate != 2048000)
+            throw ApiError(DABMOD_B200_EINVAL, "fixed point doesn't support resampler");
+        // OfdmGeneratorFixed has no CFR; CicEqualizer has no fixed-point variant (it would read the
+        // complexfix carriers as floats in the reference)
+        if (c.cfr_enable) throw ApiError(DABMOD_B200_EINVAL, "fixed point doesn't support crest factor reduction");
+        if (c.clock_rate != 0) throw ApiError(DABMOD_B200_EUNSUPPORTED, "fixed point: CicEqualizer is float only");
+        if (c.format != DABMOD_B200_FMT_COMPLEXF && c.format != DABMOD_B200_FMT_S16)
+            throw ApiError(DABMOD_B200_EINVAL, "fixed point output is s16");
+        if (2 * c.window_overlap > FX_MAX_WINDOW)
+            throw ApiError(DABMOD_B200_EUNSUPPORTED, "windowlen above " + std::to_string(FX_MAX_WINDOW / 2));
+    }
 }
 
 int guard(const std::function<void()> &fn)
@@ -1019,6 +1155,15 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
         std::stringstream ss(value);
         ss.exceptions(std::stringstream::failbit | std::stringstream::badbit);
         dabmod_b200_config &c = h->cfg;
+        if (h->fixed() && (n == "cfr" || n == "clip" || n == "errorclip" || n == "taps" || n == "coefs" ||
+                           n == "digital" || n == "mode" || n == "var"))
+            throw ApiError(DABMOD_B200_EINVAL, "Parameter '" + n + "' is not exported by the fixed-point chain "
+                                               "(no GainControl / CFR / FIRFilter / MemlessPoly there)");
+        if (h->fixed() && n == "windowlen") {
+            int v = 0;
+            std::stringstream(value) >> v;
+            if (2 * v > FX_MAX_WINDOW) throw ApiError(DABMOD_B200_EUNSUPPORTED, "windowlen above " + std::to_string(FX_MAX_WINDOW / 2));
+        }
         try {
             if (n == "digital") { ss >> c.digital_gain; }
             else if (n == "profile") { int v; ss >> v; h->profile = v != 0; }

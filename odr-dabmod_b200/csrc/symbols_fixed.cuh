@@ -1,0 +1,264 @@
+// k_symbols_fix: the symbol kernel of the FIXED-POINT engine: the chain
+// DabModulator wires for FFTEngine::KISS (src/DabModulator.cpp:144-224) --
+//   QpskSymbolMapper / PhaseReference / FrequencyInterleaver / DifferentialModulator on complexfix
+//   = std::complex<fpm::fixed<int16, int32, 14>> (src/Buffer.h:42-43), NullSymbol / TII,
+//   OfdmGeneratorFixed (src/OfdmGenerator.cpp:467-579: the vendored KISS FFT with FIXED_POINT=16),
+//   no GainControl, GuardIntervalInserter do_process<complexfix> (src/GuardIntervalInserter.cpp:115-323)
+// -- bits in, int16 I/Q out, every bit equal to the reference's.
+//
+// * Carriers: the fixed-point product chain of the differential modulator only visits
+//   {0, +-11585, +-16384} (11585 = fixed(1/sqrt 2); fpm's rounding multiply gives 11585^2 -> 8192,
+//   16384 * 11585 -> 11585), the images of the float chain's {0, +-1/sqrt2, +-1}: the same integer
+//   phase arithmetic as k_symbols (units of pi/4) with an 8-entry int16 value table.
+// * IFFT: KISS is a decimation-in-time transform (kiss_fft.c:236-291): the input is read in
+//   mixed-radix digit-reversed order into the output array, then one pass of radix-2 (N = 2048, 512)
+//   and passes of radix-4 butterflies run in place from the smallest sub-transform up, each dividing
+//   its inputs by the radix (DIVSCALAR: x * (32767 / p), rounded, >> 15) and rounding every twiddle
+//   product once (C_MUL / sround).  Integer rounding is not associative, so the kernel performs exactly
+//   these operations in exactly this order (kf_bfly2 / kf_bfly4 below), on int16 pairs in shared
+//   memory; the carriers are scattered straight to their digit-reversed positions.
+// * A CTA works on one (TF, chunk of symbol groups); a group is 2048 / N symbols side by side in one
+//   2048-point buffer, so every mode keeps all threads busy (512 radix-4 butterflies per pass).
+// * Windowing: symbol l's rising edge (2W samples around its start) is ADDED to the falling edge of
+//   symbol l-1, both multiplied by the fixed(raised cosine) window with fpm's rounding multiply;
+//   the falling edge comes from the previous symbol of the group or from a shared tail kept across
+//   groups (one chunk per TF when W > 0).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dabmod {
+
+constexpr int FX_THREADS = 256;
+constexpr int FX_POINTS = 2048;
+constexpr int FX_MAX_STAGES = 8;
+constexpr int FX_MAX_WINDOW = 1024;           // 2 W <= 2 * (sym_size - N) of TM I = 1008
+
+struct FixParams {
+    int L, K, N, null_size, sym_size, tf_in_bytes, tf_samples;
+    int G, n_groups, groups_per_chunk, n_chunks;
+    const uint16_t *pos_of_src;   // K: digit-reversed position (within its symbol) of the bin source carrier j goes to
+    const uint8_t *phase0;        // K: phase reference, units of pi/4
+    const short2 *tw;             // N: kiss twiddles, kf_cexp(+2 pi i / N)
+    int n_stages;                 // kf_factor's list, executed from the last entry to the first
+    int stage_p[FX_MAX_STAGES], stage_m[FX_MAX_STAGES];
+    int tii_count, tii_parity;
+    const uint16_t *tii_pos;      // digit-reversed positions of the TII carriers
+    const short2 *tii_val;
+    int window;                   // windowOverlap W
+    const short *window_tab;      // 2W fixed-point window values (rising edge)
+    const uint8_t *bits;
+    short2 *out;
+    unsigned long long tf_offset;
+};
+
+struct FixSmem {
+    short2 buf[FX_POINTS];
+    short2 tw[FX_POINTS];
+    uint32_t spread[256];
+    short2 c8[8];
+    short2 tail[FX_MAX_WINDOW];   // falling edge of the last symbol of the previous group
+    short win[FX_MAX_WINDOW];
+};
+
+// fpm::fixed<int16, int32, 14>::operator*= with rounding (fpm/fixed.hpp:156-169)
+__device__ __forceinline__ short fx_mul(short a, short b)
+{
+    const int v = ((int)a * (int)b) / 8192;       // truncating division, like the reference
+    return (short)(v / 2 + v % 2);
+}
+__device__ __forceinline__ short fx_sround(int x) { return (short)((x + (1 << 14)) >> 15); }
+__device__ __forceinline__ short2 fx_fixdiv(short2 c, int k)      // C_FIXDIV: k = 32767 / radix
+{
+    return make_short2(fx_sround((int)c.x * k), fx_sround((int)c.y * k));
+}
+__device__ __forceinline__ short2 fx_cmul(short2 a, short2 b)     // C_MUL
+{
+    return make_short2(fx_sround((int)a.x * b.x - (int)a.y * b.y), fx_sround((int)a.x * b.y + (int)a.y * b.x));
+}
+__device__ __forceinline__ short2 fx_add(short2 a, short2 b) { return make_short2((short)(a.x + b.x), (short)(a.y + b.y)); }
+__device__ __forceinline__ short2 fx_sub(short2 a, short2 b) { return make_short2((short)(a.x - b.x), (short)(a.y - b.y)); }
+
+// out-position of symbol s inside the TF and its length
+__device__ __forceinline__ int fx_pos(const FixParams &p, int s) { return s == 0 ? 0 : p.null_size + (s - 1) * p.sym_size; }
+__device__ __forceinline__ int fx_size(const FixParams &p, int s) { return s == 0 ? p.null_size : p.sym_size; }
+
+// sample at offset o (may be negative or beyond the symbol: cyclic extension) of a symbol whose
+// N samples start at x and whose cyclic prefix is `pre` long
+__device__ __forceinline__ short2 fx_cyclic(const short2 *x, int N, int pre, int o)
+{
+    int ix = (o - pre) % N;
+    if (ix < 0) ix += N;
+    return x[ix];
+}
+
+__global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constant__ FixParams p)
+{
+    __shared__ FixSmem sm;
+    const int tid = threadIdx.x;
+    const int N = p.N, K = p.K, G = p.G;
+    const int K16 = K / 16;                    // 16-carrier work items per symbol
+    const int tf = blockIdx.x / p.n_chunks;
+    const int chunk = blockIdx.x - tf * p.n_chunks;
+    const int grp0 = chunk * p.groups_per_chunk;
+    const int grp1 = min(grp0 + p.groups_per_chunk, p.n_groups);
+    const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
+    short2 *out = p.out + (size_t)tf * p.tf_samples;
+    const bool tii_on = p.tii_count > 0 && (((p.tf_offset + tf + p.tii_parity) & 1) == 0);
+    const int W = p.window;
+
+    // ---- per-CTA tables ----
+    for (int i = tid; i < N; i += FX_THREADS) sm.tw[i] = __ldg(p.tw + i);
+    for (int b = tid; b < 256; b += FX_THREADS) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int n = 0; n < 8; n++) s |= ((b >> (7 - n)) & 1u) << (4 * n);
+        sm.spread[b] = s;
+    }
+    if (tid < 8) {
+        // fixed(1) = 16384, fixed(M_SQRT1_2) = 11585 (QpskSymbolMapper.cpp:60, PhaseReference.cpp:139-150)
+        const short c[8] = {16384, 11585, 0, -11585, -16384, -11585, 0, 11585};
+        sm.c8[tid] = make_short2(c[tid], c[(tid + 6) & 7]);
+    }
+    for (int i = tid; i < 2 * W; i += FX_THREADS) {
+        sm.win[i] = __ldg(p.window_tab + i);
+        sm.tail[i] = make_short2(0, 0);
+    }
+
+    // ---- carrier work item of this thread: symbol cg of the group, carriers 16*jj .. 16*jj+15 ----
+    const int cg = tid / K16, jj = tid - cg * K16;
+    const bool carrier_thread = tid < G * K16;
+    uint32_t ph_lo = 0, ph_hi = 0;             // nibble-packed running phase, carriers 0-7 / 8-15
+    if (carrier_thread) {
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+            ph_lo |= (uint32_t)__ldg(p.phase0 + 16 * jj + n) << (4 * n);
+            ph_hi |= (uint32_t)__ldg(p.phase0 + 16 * jj + 8 + n) << (4 * n);
+        }
+    }
+    __syncthreads();
+    // phase prefix: data symbol d = s - 2 for s >= 2; consume the rows before the chunk
+    if (carrier_thread) {
+        const int nd = max(0, grp0 * G - 2);
+        const uint8_t *row = bits + 2 * jj;
+        for (int d = 0; d < nd; d++, row += K / 4) {
+            const unsigned iw = __ldg(reinterpret_cast<const unsigned short *>(row));
+            const unsigned qw = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
+            ph_lo = (ph_lo + 0x11111111u + 2u * sm.spread[(iw ^ qw) & 0xff] + 4u * sm.spread[qw & 0xff]) & 0x77777777u;
+            ph_hi = (ph_hi + 0x11111111u + 2u * sm.spread[((iw ^ qw) >> 8) & 0xff] + 4u * sm.spread[qw >> 8]) & 0x77777777u;
+        }
+    }
+
+    for (int grp = grp0; grp < grp1; grp++) {
+        const int s0 = grp * G;
+        // ---- 1. carriers into their digit-reversed positions; everything else is zero ----
+        for (int i = tid; i < FX_POINTS; i += FX_THREADS) sm.buf[i] = make_short2(0, 0);
+        __syncthreads();
+        if (carrier_thread) {
+            uint32_t my_lo = 0, my_hi = 0;
+            bool mine = false;
+            for (int g = 0; g < G; g++) {
+                const int s = s0 + g;
+                if (s >= 2 && s <= p.L) {
+                    const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
+                    const unsigned iw = __ldg(reinterpret_cast<const unsigned short *>(row));
+                    const unsigned qw = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
+                    ph_lo = (ph_lo + 0x11111111u + 2u * sm.spread[(iw ^ qw) & 0xff] + 4u * sm.spread[qw & 0xff]) & 0x77777777u;
+                    ph_hi = (ph_hi + 0x11111111u + 2u * sm.spread[((iw ^ qw) >> 8) & 0xff] + 4u * sm.spread[qw >> 8]) & 0x77777777u;
+                }
+                if (g == cg) { my_lo = ph_lo; my_hi = ph_hi; mine = s >= 1 && s <= p.L; }
+            }
+            if (mine) {
+#pragma unroll
+                for (int n = 0; n < 16; n++) {
+                    const unsigned ph = ((n < 8 ? my_lo >> (4 * n) : my_hi >> (4 * (n - 8)))) & 7u;
+                    sm.buf[cg * N + __ldg(p.pos_of_src + 16 * jj + n)] = sm.c8[ph];
+                }
+            }
+        }
+        if (grp == 0 && tii_on && tid < p.tii_count) sm.buf[__ldg(p.tii_pos + tid)] = __ldg(p.tii_val + tid);
+        __syncthreads();
+
+        // ---- 2. KISS inverse FFT, in place, smallest sub-transforms first ----
+        for (int st = p.n_stages - 1; st >= 0; st--) {
+            const int radix = p.stage_p[st], m = p.stage_m[st];
+            const int fstride = N / (radix * m);
+            if (radix == 4) {
+#pragma unroll
+                for (int i = 0; i < FX_POINTS / 4 / FX_THREADS; i++) {
+                    const int b = tid + FX_THREADS * i;
+                    const int blk = b / m, k = b - blk * m;       // over all G symbols: blocks of 4m points tile the buffer
+                    short2 *F = sm.buf + blk * 4 * m + k;
+                    short2 f0 = fx_fixdiv(F[0], 32767 / 4), f1 = fx_fixdiv(F[m], 32767 / 4);
+                    short2 f2 = fx_fixdiv(F[2 * m], 32767 / 4), f3 = fx_fixdiv(F[3 * m], 32767 / 4);
+                    const short2 a0 = fx_cmul(f1, sm.tw[fstride * k]);
+                    const short2 a1 = fx_cmul(f2, sm.tw[fstride * 2 * k]);
+                    const short2 a2 = fx_cmul(f3, sm.tw[fstride * 3 * k]);
+                    const short2 a5 = fx_sub(f0, a1);
+                    f0 = fx_add(f0, a1);
+                    const short2 a3 = fx_add(a0, a2), a4 = fx_sub(a0, a2);
+                    F[2 * m] = fx_sub(f0, a3);
+                    F[0] = fx_add(f0, a3);
+                    F[m] = make_short2((short)(a5.x - a4.y), (short)(a5.y + a4.x));
+                    F[3 * m] = make_short2((short)(a5.x + a4.y), (short)(a5.y - a4.x));
+                }
+            }
+            else {
+#pragma unroll
+                for (int i = 0; i < FX_POINTS / 2 / FX_THREADS; i++) {
+                    const int b = tid + FX_THREADS * i;
+                    const int blk = b / m, k = b - blk * m;
+                    short2 *F = sm.buf + blk * 2 * m + k;
+                    const short2 f0 = fx_fixdiv(F[0], 32767 / 2), f1 = fx_fixdiv(F[m], 32767 / 2);
+                    const short2 t = fx_cmul(f1, sm.tw[fstride * k]);
+                    F[m] = fx_sub(f0, t);
+                    F[0] = fx_add(f0, t);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- 3. guard interval (+ window) and store ----
+        for (int g = 0; g < G; g++) {
+            const int s = s0 + g;
+            if (s > p.L) break;
+            const short2 *x = sm.buf + g * N;
+            const int size = fx_size(p, s), pre = size - N, pos = fx_pos(p, s);
+            const bool first = s == 0, last = s == p.L;
+            const int lo = (W > 0 && !first) ? -W : 0;
+            const int hi = (W > 0 && !last) ? size - W : size;
+            for (int o = lo + tid; o < hi; o += FX_THREADS) {
+                short2 v = fx_cyclic(x, N, pre, o);
+                if (W > 0 && !first && o < W) {
+                    const short wr = sm.win[o + W];
+                    v = make_short2(fx_mul(v.x, wr), fx_mul(v.y, wr));
+                    short2 f;                                      // falling edge of symbol s - 1 at the same place
+                    if (g > 0) {
+                        const int psize = fx_size(p, s - 1);
+                        const short wf = sm.win[W - 1 - o];       // = w[2W - 1 - (o' - (psize - W))], o' = psize + o
+                        const short2 u = fx_cyclic(x - N, N, psize - N, psize + o);
+                        f = make_short2(fx_mul(u.x, wf), fx_mul(u.y, wf));
+                    }
+                    else f = sm.tail[o + W];
+                    v = fx_add(v, f);
+                }
+                out[pos + o] = v;
+            }
+        }
+        if (W > 0) {
+            // falling edge of the group's last symbol for the next group
+            const int s = min(s0 + G - 1, p.L);
+            const short2 *x = sm.buf + (s - s0) * N;
+            const int size = fx_size(p, s), pre = size - N;
+            __syncthreads();                                       // sm.tail was read above
+            for (int i = tid; i < 2 * W; i += FX_THREADS) {
+                const short2 u = fx_cyclic(x, N, pre, size - W + i);
+                const short wf = sm.win[2 * W - 1 - i];
+                sm.tail[i] = make_short2(fx_mul(u.x, wf), fx_mul(u.y, wf));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+} // namespace dabmod
