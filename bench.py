@@ -217,6 +217,7 @@ def other_configs():
         ("c4 TM II native", dict(mode=2), 4096),
         ("c4 TM III native", dict(mode=3), 4096),
         ("c4 TM IV native", dict(mode=4), 2048),
+        ("n4 TM I fixed-point engine (FFTEngine::KISS), int16 I/Q", dict(mode=1, fixed_point=True), 1024),
     ]
 
 
@@ -259,6 +260,25 @@ def measure_config(dm, torch, name, kw, n_tf, stream, peak, steps=5, warmup=3):
                             "frac_of_hbm_peak": byt / t / 1e9 / peak,
                             "algorithmic_TFLOP/s_fp32": n_tf * info["flop"] / t / 1e12,
                             "note": "FP32-bound stage (17-19 flop/B > the 11 flop/B ridge): see DESIGN.md"}
+    if kw.get("fixed_point"):
+        t = float(np.mean(kt["k_symbols_fix"])) * 1e-3
+        byt = n_tf * (mod.tf_in_bytes + mod.tf_out_bytes)        # bits in, int16 I/Q out
+        res["symbols_fix"] = {"ms": t * 1e3, "algorithmic_GB/s": byt / t / 1e9, "frac_of_hbm_peak": byt / t / 1e9 / peak,
+                              "note": "integer kernel (KISS FIXED_POINT=16 arithmetic, bit-exact), ALU/LSU bound"}
+        try:
+            from oracle import refwrap
+            if refwrap.available():
+                ref = refwrap.RefChain(mode=mode, fixed_point=True)
+                hb = bits[:16].cpu().numpy()
+                ref.feed_raw(hb[0])
+                t0 = time.perf_counter()
+                for b in hb:
+                    ref.feed_raw(b)
+                dt = time.perf_counter() - t0
+                res["cpu_reference"] = {"eti_frames_per_s": len(hb) * ETI_PER_TF_MODE[mode] / dt, "cores": 1,
+                                        "kind": "reference", "sample": "16 TFs through the reference's fixed-point chain"}
+        except Exception as e:
+            res["cpu_reference"] = {"error": str(e)}
     mod.close()
     del bits, out
     torch.cuda.empty_cache()

@@ -88,6 +88,9 @@ B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format,
     c.tii_comb = s.tiiConfig.comb;
     c.tii_pattern = s.tiiConfig.pattern;
     c.tii_old_variant = s.tiiConfig.old_variant;
+    /* fftEngine = KISS selects the fixed-point chain (DabModulator.cpp:144,194-224); DEXTER is an FPGA */
+    if (s.fftEngine == FFTEngine::KISS) c.fft_engine = DABMOD_B200_FFT_KISS_FIXED;
+    else if (s.fftEngine != FFTEngine::FFTW) throw std::runtime_error("B200OfdmChain: unsupported fft engine");
 
     std::vector<float> taps, coefs;
     if (!s.filterTapsFilename.empty()) {

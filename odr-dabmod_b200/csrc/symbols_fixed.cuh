@@ -67,17 +67,51 @@ __device__ __forceinline__ short fx_mul(short a, short b)
     const int v = ((int)a * (int)b) / 8192;       // truncating division, like the reference
     return (short)(v / 2 + v % 2);
 }
-__device__ __forceinline__ short fx_sround(int x) { return (short)((x + (1 << 14)) >> 15); }
-__device__ __forceinline__ short2 fx_fixdiv(short2 c, int k)      // C_FIXDIV: k = 32767 / radix
+
+// KISS arithmetic on int pairs.  The reference keeps every intermediate in an int16 (kiss_fft_cpx), i.e.
+// reduces it mod 2^16; additions and subtractions commute with that reduction, so the butterflies below work
+// on 32-bit values and reduce only where it matters: when a value is loaded (sign extension of the stored
+// int16) before it enters a multiplication, and when it is stored (the low 16 bits).  DIVSCALAR and C_MUL
+// results of in-range operands fit an int16 by construction (|x| <= 32767 -> |x * 8191 >> 15| <= 8192,
+// twiddles <= 32767), so they need no reduction either.
+struct fxc { int x, y; };
+__device__ __forceinline__ fxc fx_unpack(uint32_t w) { return fxc{(int)(w << 16) >> 16, (int)w >> 16}; }
+__device__ __forceinline__ uint32_t fx_pack(fxc c) { return __byte_perm((uint32_t)c.x, (uint32_t)c.y, 0x5410); }
+__device__ __forceinline__ int fx_sround(int x) { return (x + (1 << 14)) >> 15; }
+__device__ __forceinline__ fxc fx_fixdiv(fxc c, int k)              // C_FIXDIV: k = 32767 / radix
 {
-    return make_short2(fx_sround((int)c.x * k), fx_sround((int)c.y * k));
+    return fxc{fx_sround(c.x * k), fx_sround(c.y * k)};
 }
-__device__ __forceinline__ short2 fx_cmul(short2 a, short2 b)     // C_MUL
+__device__ __forceinline__ fxc fx_cmul(fxc a, fxc b)               // C_MUL
 {
-    return make_short2(fx_sround((int)a.x * b.x - (int)a.y * b.y), fx_sround((int)a.x * b.y + (int)a.y * b.x));
+    return fxc{fx_sround(a.x * b.x - a.y * b.y), fx_sround(a.x * b.y + a.y * b.x)};
 }
-__device__ __forceinline__ short2 fx_add(short2 a, short2 b) { return make_short2((short)(a.x + b.x), (short)(a.y + b.y)); }
-__device__ __forceinline__ short2 fx_sub(short2 a, short2 b) { return make_short2((short)(a.x - b.x), (short)(a.y - b.y)); }
+__device__ __forceinline__ fxc fx_add(fxc a, fxc b) { return fxc{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ fxc fx_sub(fxc a, fxc b) { return fxc{a.x - b.x, a.y - b.y}; }
+
+// kf_bfly4 with st->inverse (kiss_fft.c:66-113) on f[0..3] = Fout[0], Fout[m], Fout[2m], Fout[3m]
+__device__ __forceinline__ void fx_bfly4(fxc (&f)[4], fxc w1, fxc w2, fxc w3)
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) f[q] = fx_fixdiv(f[q], 32767 / 4);
+    const fxc a0 = fx_cmul(f[1], w1), a1 = fx_cmul(f[2], w2), a2 = fx_cmul(f[3], w3);
+    const fxc a5 = fx_sub(f[0], a1);
+    const fxc t0 = fx_add(f[0], a1);
+    const fxc a3 = fx_add(a0, a2), a4 = fx_sub(a0, a2);
+    f[2] = fx_sub(t0, a3);
+    f[0] = fx_add(t0, a3);
+    f[1] = fxc{a5.x - a4.y, a5.y + a4.x};
+    f[3] = fxc{a5.x + a4.y, a5.y - a4.x};
+}
+// kf_bfly2 (kiss_fft.c:40-64)
+__device__ __forceinline__ void fx_bfly2(fxc &f0, fxc &f1, fxc w)
+{
+    f0 = fx_fixdiv(f0, 32767 / 2);
+    f1 = fx_fixdiv(f1, 32767 / 2);
+    const fxc t = fx_cmul(f1, w);
+    f1 = fx_sub(f0, t);
+    f0 = fx_add(f0, t);
+}
 
 // out-position of symbol s inside the TF and its length
 __device__ __forceinline__ int fx_pos(const FixParams &p, int s) { return s == 0 ? 0 : p.null_size + (s - 1) * p.sym_size; }
@@ -87,9 +121,7 @@ __device__ __forceinline__ int fx_size(const FixParams &p, int s) { return s == 
 // N samples start at x and whose cyclic prefix is `pre` long
 __device__ __forceinline__ short2 fx_cyclic(const short2 *x, int N, int pre, int o)
 {
-    int ix = (o - pre) % N;
-    if (ix < 0) ix += N;
-    return x[ix];
+    return x[(o - pre) & (N - 1)];             // N is a power of two
 }
 
 __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constant__ FixParams p)
@@ -181,38 +213,33 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
 
         // ---- 2. KISS inverse FFT, in place, smallest sub-transforms first ----
         for (int st = p.n_stages - 1; st >= 0; st--) {
+            // (radix and m are powers of two: shifts instead of divisions)
             const int radix = p.stage_p[st], m = p.stage_m[st];
-            const int fstride = N / (radix * m);
+            const int lm = 31 - __clz(m);
+            const int fstride = N >> (lm + (radix == 4 ? 2 : 1));
+            uint32_t *buf32 = reinterpret_cast<uint32_t *>(sm.buf);
+            const uint32_t *tw32 = reinterpret_cast<const uint32_t *>(sm.tw);
             if (radix == 4) {
 #pragma unroll
                 for (int i = 0; i < FX_POINTS / 4 / FX_THREADS; i++) {
                     const int b = tid + FX_THREADS * i;
-                    const int blk = b / m, k = b - blk * m;       // over all G symbols: blocks of 4m points tile the buffer
-                    short2 *F = sm.buf + blk * 4 * m + k;
-                    short2 f0 = fx_fixdiv(F[0], 32767 / 4), f1 = fx_fixdiv(F[m], 32767 / 4);
-                    short2 f2 = fx_fixdiv(F[2 * m], 32767 / 4), f3 = fx_fixdiv(F[3 * m], 32767 / 4);
-                    const short2 a0 = fx_cmul(f1, sm.tw[fstride * k]);
-                    const short2 a1 = fx_cmul(f2, sm.tw[fstride * 2 * k]);
-                    const short2 a2 = fx_cmul(f3, sm.tw[fstride * 3 * k]);
-                    const short2 a5 = fx_sub(f0, a1);
-                    f0 = fx_add(f0, a1);
-                    const short2 a3 = fx_add(a0, a2), a4 = fx_sub(a0, a2);
-                    F[2 * m] = fx_sub(f0, a3);
-                    F[0] = fx_add(f0, a3);
-                    F[m] = make_short2((short)(a5.x - a4.y), (short)(a5.y + a4.x));
-                    F[3 * m] = make_short2((short)(a5.x + a4.y), (short)(a5.y - a4.x));
+                    const int blk = b >> lm, k = b & (m - 1);     // over all G symbols: blocks of 4m points tile the buffer
+                    uint32_t *F = buf32 + blk * 4 * m + k;
+                    fxc f[4] = {fx_unpack(F[0]), fx_unpack(F[m]), fx_unpack(F[2 * m]), fx_unpack(F[3 * m])};
+                    fx_bfly4(f, fx_unpack(tw32[fstride * k]), fx_unpack(tw32[fstride * 2 * k]),
+                             fx_unpack(tw32[fstride * 3 * k]));
+                    F[0] = fx_pack(f[0]); F[m] = fx_pack(f[1]); F[2 * m] = fx_pack(f[2]); F[3 * m] = fx_pack(f[3]);
                 }
             }
             else {
 #pragma unroll
                 for (int i = 0; i < FX_POINTS / 2 / FX_THREADS; i++) {
                     const int b = tid + FX_THREADS * i;
-                    const int blk = b / m, k = b - blk * m;
-                    short2 *F = sm.buf + blk * 2 * m + k;
-                    const short2 f0 = fx_fixdiv(F[0], 32767 / 2), f1 = fx_fixdiv(F[m], 32767 / 2);
-                    const short2 t = fx_cmul(f1, sm.tw[fstride * k]);
-                    F[m] = fx_sub(f0, t);
-                    F[0] = fx_add(f0, t);
+                    const int blk = b >> lm, k = b & (m - 1);
+                    uint32_t *F = buf32 + blk * 2 * m + k;
+                    fxc f0 = fx_unpack(F[0]), f1 = fx_unpack(F[m]);
+                    fx_bfly2(f0, f1, fx_unpack(tw32[fstride * k]));
+                    F[0] = fx_pack(f0); F[m] = fx_pack(f1);
                 }
             }
             __syncthreads();
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
                         f = make_short2(fx_mul(u.x, wf), fx_mul(u.y, wf));
                     }
                     else f = sm.tail[o + W];
-                    v = fx_add(v, f);
+                    v = make_short2((short)(v.x + f.x), (short)(v.y + f.y));
                 }
                 out[pos + o] = v;
             }
