@@ -730,7 +730,13 @@ void enqueue_fixed(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     fp.out = reinterpret_cast<short2 *>(dst);
     fp.tf_offset = stream_tf;
     ProfScope prof(h, "k_symbols_fix", s);
-    k_symbols_fix<<<(unsigned)(n_tf * fp.n_chunks), FX_THREADS, 0, s>>>(fp);
+    const unsigned grid = (unsigned)(n_tf * fp.n_chunks);
+    switch (m.N) {
+        case 2048: k_symbols_fix<2048><<<grid, FX_THREADS, 0, s>>>(fp); break;
+        case 1024: k_symbols_fix<1024><<<grid, FX_THREADS, 0, s>>>(fp); break;
+        case 512: k_symbols_fix<512><<<grid, FX_THREADS, 0, s>>>(fp); break;
+        default: k_symbols_fix<256><<<grid, FX_THREADS, 0, s>>>(fp); break;
+    }
     CUDA_CHECK(cudaGetLastError());
     prof.end();
     launches++;

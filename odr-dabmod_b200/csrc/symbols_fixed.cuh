@@ -29,10 +29,14 @@
 
 namespace dabmod {
 
-constexpr int FX_THREADS = 256;
+constexpr int FX_THREADS = 128;
 constexpr int FX_POINTS = 2048;
 constexpr int FX_MAX_STAGES = 8;
 constexpr int FX_MAX_WINDOW = 1024;           // 2 W <= 2 * (sym_size - N) of TM I = 1008
+// Shared-memory index padding: 8 words after every 128.  A fused pass walks the buffer at strides of
+// 8 / 16 / 128 points; without the skew the 128-point blocks of one warp's tasks would alias on the banks.
+__device__ __host__ __forceinline__ constexpr int fxpad(int i) { return i + ((i >> 7) << 3); }
+constexpr int FX_BUF = FX_POINTS + FX_POINTS / 16;
 
 struct FixParams {
     int L, K, N, null_size, sym_size, tf_in_bytes, tf_samples;
@@ -53,7 +57,7 @@ struct FixParams {
 };
 
 struct FixSmem {
-    short2 buf[FX_POINTS];
+    uint32_t buf[FX_BUF];         // int16 pairs, fxpad layout
     short2 tw[FX_POINTS];
     uint32_t spread[256];
     short2 c8[8];
@@ -113,23 +117,128 @@ __device__ __forceinline__ void fx_bfly2(fxc &f0, fxc &f1, fxc w)
     f0 = fx_add(f0, t);
 }
 
+// ---- fused passes: two KISS stages per trip through shared memory --------------------------------
+// Stages run smallest sub-transform first (kf_work's recursion unwinds that way); a butterfly of the
+// second stage needs four outputs of the first, so a thread that owns 16 points k + MA j (j < 16) of one
+// 16 MA block can do four butterflies of the stage with m = MA and then four of the stage with m = 4 MA.
+// Every butterfly is exactly kf_bfly4 / kf_bfly2: fusing only changes where the values wait in between.
+
+// radix 2 (m = 1) then radix 4 (m = 2): 8 contiguous points
+template <int N>
+__device__ __forceinline__ void fx_pass_24(uint32_t *buf, const uint32_t *tw, int task)
+{
+    uint4 *v = reinterpret_cast<uint4 *>(buf + fxpad(8 * task));
+    const uint4 lo = v[0], hi = v[1];
+    fxc f[8] = {fx_unpack(lo.x), fx_unpack(lo.y), fx_unpack(lo.z), fx_unpack(lo.w),
+                fx_unpack(hi.x), fx_unpack(hi.y), fx_unpack(hi.z), fx_unpack(hi.w)};
+    const fxc w0 = fx_unpack(tw[0]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) fx_bfly2(f[2 * i], f[2 * i + 1], w0);
+    constexpr int fsb = N / 8;
+#pragma unroll
+    for (int kb = 0; kb < 2; kb++) {
+        fxc g[4] = {f[kb], f[kb + 2], f[kb + 4], f[kb + 6]};
+        fx_bfly4(g, fx_unpack(tw[fsb * kb]), fx_unpack(tw[fsb * 2 * kb]), fx_unpack(tw[fsb * 3 * kb]));
+        f[kb] = g[0]; f[kb + 2] = g[1]; f[kb + 4] = g[2]; f[kb + 6] = g[3];
+    }
+    v[0] = make_uint4(fx_pack(f[0]), fx_pack(f[1]), fx_pack(f[2]), fx_pack(f[3]));
+    v[1] = make_uint4(fx_pack(f[4]), fx_pack(f[5]), fx_pack(f[6]), fx_pack(f[7]));
+}
+
+// radix 4 (m = MA) then radix 4 (m = 4 MA): points k + MA j, j < 16, of one 16 MA block
+template <int N, int MA>
+__device__ __forceinline__ void fx_pass_44(uint32_t *buf, const uint32_t *tw, int task)
+{
+    const int blk = task / MA, k = task % MA;
+    const int base = blk * 16 * MA + k;
+    fxc f[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) f[j] = fx_unpack(buf[fxpad(base + j * MA)]);
+    constexpr int fsa = N / (4 * MA), fsb = N / (16 * MA);
+    {
+        const fxc w1 = fx_unpack(tw[fsa * k]), w2 = fx_unpack(tw[fsa * 2 * k]), w3 = fx_unpack(tw[fsa * 3 * k]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            fxc g[4] = {f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]};
+            fx_bfly4(g, w1, w2, w3);
+            f[4 * i] = g[0]; f[4 * i + 1] = g[1]; f[4 * i + 2] = g[2]; f[4 * i + 3] = g[3];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int kb = k + i * MA;
+        fxc g[4] = {f[i], f[i + 4], f[i + 8], f[i + 12]};
+        fx_bfly4(g, fx_unpack(tw[fsb * kb]), fx_unpack(tw[fsb * 2 * kb]), fx_unpack(tw[fsb * 3 * kb]));
+        f[i] = g[0]; f[i + 4] = g[1]; f[i + 8] = g[2]; f[i + 12] = g[3];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) buf[fxpad(base + j * MA)] = fx_pack(f[j]);
+}
+
+// one radix 4 stage (m = M)
+template <int N, int M>
+__device__ __forceinline__ void fx_pass_4(uint32_t *buf, const uint32_t *tw, int b)
+{
+    const int blk = b / M, k = b % M;
+    const int base = blk * 4 * M + k;
+    constexpr int fs = N / (4 * M);
+    fxc g[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) g[q] = fx_unpack(buf[fxpad(base + q * M)]);
+    fx_bfly4(g, fx_unpack(tw[fs * k]), fx_unpack(tw[fs * 2 * k]), fx_unpack(tw[fs * 3 * k]));
+#pragma unroll
+    for (int q = 0; q < 4; q++) buf[fxpad(base + q * M)] = fx_pack(g[q]);
+}
+
+// The mode's transform(s): G = 2048 / N symbols side by side; kf_factor gives
+//   2048: 4 4 4 4 4 2    1024: 4 4 4 4 4    512: 4 4 4 4 2    256: 4 4 4 4     (executed right to left)
+template <int N>
+__device__ __forceinline__ void fx_ifft(uint32_t *buf, const uint32_t *tw, int tid)
+{
+    if (N == 2048 || N == 512) {
+#pragma unroll
+        for (int i = 0; i < FX_POINTS / 8 / FX_THREADS; i++) fx_pass_24<N>(buf, tw, tid + FX_THREADS * i);
+        __syncthreads();
+        fx_pass_44<N, 8>(buf, tw, tid);
+        __syncthreads();
+        if (N == 2048) fx_pass_44<N, 128>(buf, tw, tid);
+        else {
+#pragma unroll
+            for (int i = 0; i < FX_POINTS / 4 / FX_THREADS; i++) fx_pass_4<N, 128>(buf, tw, tid + FX_THREADS * i);
+        }
+    }
+    else {
+        fx_pass_44<N, 1>(buf, tw, tid);
+        __syncthreads();
+        fx_pass_44<N, 16>(buf, tw, tid);
+        if (N == 1024) {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < FX_POINTS / 4 / FX_THREADS; i++) fx_pass_4<N, 256>(buf, tw, tid + FX_THREADS * i);
+        }
+    }
+    __syncthreads();
+}
+
 // out-position of symbol s inside the TF and its length
 __device__ __forceinline__ int fx_pos(const FixParams &p, int s) { return s == 0 ? 0 : p.null_size + (s - 1) * p.sym_size; }
 __device__ __forceinline__ int fx_size(const FixParams &p, int s) { return s == 0 ? p.null_size : p.sym_size; }
 
 // sample at offset o (may be negative or beyond the symbol: cyclic extension) of a symbol whose
 // N samples start at x and whose cyclic prefix is `pre` long
-__device__ __forceinline__ short2 fx_cyclic(const short2 *x, int N, int pre, int o)
+__device__ __forceinline__ short2 fx_cyclic(const uint32_t *buf, int x0, int N, int pre, int o)
 {
-    return x[(o - pre) & (N - 1)];             // N is a power of two
+    const uint32_t w = buf[fxpad(x0 + ((o - pre) & (N - 1)))];    // N is a power of two
+    return make_short2((short)(w & 0xffffu), (short)(w >> 16));
 }
 
+template <int N>
 __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constant__ FixParams p)
 {
-    __shared__ FixSmem sm;
+    __shared__ __align__(16) FixSmem sm;
     const int tid = threadIdx.x;
-    const int N = p.N, K = p.K, G = p.G;
-    const int K16 = K / 16;                    // 16-carrier work items per symbol
+    constexpr int K = N * 3 / 4, G = FX_POINTS / N;
+    constexpr int K16 = K / 16;                    // 16-carrier work items per symbol
     const int tf = blockIdx.x / p.n_chunks;
     const int chunk = blockIdx.x - tf * p.n_chunks;
     const int grp0 = chunk * p.groups_per_chunk;
@@ -184,7 +293,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
     for (int grp = grp0; grp < grp1; grp++) {
         const int s0 = grp * G;
         // ---- 1. carriers into their digit-reversed positions; everything else is zero ----
-        for (int i = tid; i < FX_POINTS; i += FX_THREADS) sm.buf[i] = make_short2(0, 0);
+        for (int i = tid; i < FX_BUF; i += FX_THREADS) sm.buf[i] = 0u;
         __syncthreads();
         if (carrier_thread) {
             uint32_t my_lo = 0, my_hi = 0;
@@ -204,58 +313,31 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
 #pragma unroll
                 for (int n = 0; n < 16; n++) {
                     const unsigned ph = ((n < 8 ? my_lo >> (4 * n) : my_hi >> (4 * (n - 8)))) & 7u;
-                    sm.buf[cg * N + __ldg(p.pos_of_src + 16 * jj + n)] = sm.c8[ph];
+                    const short2 c = sm.c8[ph];
+                    sm.buf[fxpad(cg * N + __ldg(p.pos_of_src + 16 * jj + n))] = (uint32_t)(uint16_t)c.x | ((uint32_t)(uint16_t)c.y << 16);
                 }
             }
         }
-        if (grp == 0 && tii_on && tid < p.tii_count) sm.buf[__ldg(p.tii_pos + tid)] = __ldg(p.tii_val + tid);
+        if (grp == 0 && tii_on && tid < p.tii_count) {
+            const short2 c = __ldg(p.tii_val + tid);
+            sm.buf[fxpad(__ldg(p.tii_pos + tid))] = (uint32_t)(uint16_t)c.x | ((uint32_t)(uint16_t)c.y << 16);
+        }
         __syncthreads();
 
         // ---- 2. KISS inverse FFT, in place, smallest sub-transforms first ----
-        for (int st = p.n_stages - 1; st >= 0; st--) {
-            // (radix and m are powers of two: shifts instead of divisions)
-            const int radix = p.stage_p[st], m = p.stage_m[st];
-            const int lm = 31 - __clz(m);
-            const int fstride = N >> (lm + (radix == 4 ? 2 : 1));
-            uint32_t *buf32 = reinterpret_cast<uint32_t *>(sm.buf);
-            const uint32_t *tw32 = reinterpret_cast<const uint32_t *>(sm.tw);
-            if (radix == 4) {
-#pragma unroll
-                for (int i = 0; i < FX_POINTS / 4 / FX_THREADS; i++) {
-                    const int b = tid + FX_THREADS * i;
-                    const int blk = b >> lm, k = b & (m - 1);     // over all G symbols: blocks of 4m points tile the buffer
-                    uint32_t *F = buf32 + blk * 4 * m + k;
-                    fxc f[4] = {fx_unpack(F[0]), fx_unpack(F[m]), fx_unpack(F[2 * m]), fx_unpack(F[3 * m])};
-                    fx_bfly4(f, fx_unpack(tw32[fstride * k]), fx_unpack(tw32[fstride * 2 * k]),
-                             fx_unpack(tw32[fstride * 3 * k]));
-                    F[0] = fx_pack(f[0]); F[m] = fx_pack(f[1]); F[2 * m] = fx_pack(f[2]); F[3 * m] = fx_pack(f[3]);
-                }
-            }
-            else {
-#pragma unroll
-                for (int i = 0; i < FX_POINTS / 2 / FX_THREADS; i++) {
-                    const int b = tid + FX_THREADS * i;
-                    const int blk = b >> lm, k = b & (m - 1);
-                    uint32_t *F = buf32 + blk * 2 * m + k;
-                    fxc f0 = fx_unpack(F[0]), f1 = fx_unpack(F[m]);
-                    fx_bfly2(f0, f1, fx_unpack(tw32[fstride * k]));
-                    F[0] = fx_pack(f0); F[m] = fx_pack(f1);
-                }
-            }
-            __syncthreads();
-        }
+        fx_ifft<N>(sm.buf, reinterpret_cast<const uint32_t *>(sm.tw), tid);
 
         // ---- 3. guard interval (+ window) and store ----
         for (int g = 0; g < G; g++) {
             const int s = s0 + g;
             if (s > p.L) break;
-            const short2 *x = sm.buf + g * N;
+            const int x0 = g * N;
             const int size = fx_size(p, s), pre = size - N, pos = fx_pos(p, s);
             const bool first = s == 0, last = s == p.L;
             const int lo = (W > 0 && !first) ? -W : 0;
             const int hi = (W > 0 && !last) ? size - W : size;
             for (int o = lo + tid; o < hi; o += FX_THREADS) {
-                short2 v = fx_cyclic(x, N, pre, o);
+                short2 v = fx_cyclic(sm.buf, x0, N, pre, o);
                 if (W > 0 && !first && o < W) {
                     const short wr = sm.win[o + W];
                     v = make_short2(fx_mul(v.x, wr), fx_mul(v.y, wr));
@@ -263,7 +345,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
                     if (g > 0) {
                         const int psize = fx_size(p, s - 1);
                         const short wf = sm.win[W - 1 - o];       // = w[2W - 1 - (o' - (psize - W))], o' = psize + o
-                        const short2 u = fx_cyclic(x - N, N, psize - N, psize + o);
+                        const short2 u = fx_cyclic(sm.buf, x0 - N, N, psize - N, psize + o);
                         f = make_short2(fx_mul(u.x, wf), fx_mul(u.y, wf));
                     }
                     else f = sm.tail[o + W];
@@ -275,11 +357,11 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
         if (W > 0) {
             // falling edge of the group's last symbol for the next group
             const int s = min(s0 + G - 1, p.L);
-            const short2 *x = sm.buf + (s - s0) * N;
+            const int x0 = (s - s0) * N;
             const int size = fx_size(p, s), pre = size - N;
             __syncthreads();                                       // sm.tail was read above
             for (int i = tid; i < 2 * W; i += FX_THREADS) {
-                const short2 u = fx_cyclic(x, N, pre, size - W + i);
+                const short2 u = fx_cyclic(sm.buf, x0, N, pre, size - W + i);
                 const short wf = sm.win[2 * W - 1 - i];
                 sm.tail[i] = make_short2(fx_mul(u.x, wf), fx_mul(u.y, wf));
             }
