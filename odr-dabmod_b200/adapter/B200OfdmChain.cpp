@@ -66,7 +66,7 @@ int load_coefs(const std::string& file, std::vector<float>& coefs)
 
 } // namespace
 
-B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format, int device) :
+B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format, int device, bool fixedPoint) :
     ModCodec(),
     RemoteControllable("b200chain")
 {
@@ -88,9 +88,8 @@ B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format,
     c.tii_comb = s.tiiConfig.comb;
     c.tii_pattern = s.tiiConfig.pattern;
     c.tii_old_variant = s.tiiConfig.old_variant;
-    /* fftEngine = KISS selects the fixed-point chain (DabModulator.cpp:144,194-224); DEXTER is an FPGA */
-    if (s.fftEngine == FFTEngine::KISS) c.fft_engine = DABMOD_B200_FFT_KISS_FIXED;
-    else if (s.fftEngine != FFTEngine::FFTW) throw std::runtime_error("B200OfdmChain: unsupported fft engine");
+    /* the fixed-point chain of DabModulator.cpp:144,194-224 (fftEngine = KISS there) */
+    if (fixedPoint || s.fftEngine == FFTEngine::KISS) c.fft_engine = DABMOD_B200_FFT_KISS_FIXED;
 
     std::vector<float> taps, coefs;
     if (!s.filterTapsFilename.empty()) {

@@ -35,7 +35,10 @@ class B200OfdmChain : public ModCodec, public RemoteControllable
 public:
     /* `format`: "" / "complexf" / "s16" / "u8" / "s8" (what DabModulator hands to
      * FormatConverter); device: CUDA ordinal. */
-    B200OfdmChain(const mod_settings_t& settings, const std::string& format, int device = 0);
+    /* fixedPoint (or settings.fftEngine == KISS) selects the fixed-point engine: the chain DabModulator builds
+     * for FFTEngine::KISS (DabModulator.cpp:144-224), int16 I/Q out, bit-exact with it */
+    B200OfdmChain(const mod_settings_t& settings, const std::string& format, int device = 0,
+                  bool fixedPoint = false);
     virtual ~B200OfdmChain();
     B200OfdmChain(const B200OfdmChain&) = delete;
     B200OfdmChain& operator=(const B200OfdmChain&) = delete;

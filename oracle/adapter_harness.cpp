@@ -47,6 +47,7 @@ struct ref_cfg {          /* same layout as oracle/ref_harness.cpp */
     const char *poly_coef_file;
     const char *format;
     const char *stop_after;   /* unused here */
+    int32_t  fixed_point;     /* 1 = fftEngine KISS: the adapter selects its fixed-point engine */
 };
 }
 
@@ -103,6 +104,7 @@ void *adp_create(const ref_cfg *c, int device)
         s.filterTapsFilename = c->fir_taps_file ? c->fir_taps_file : "";
         s.polyCoefFilename = c->poly_coef_file ? c->poly_coef_file : "";
         s.showProcessTime = false;
+        if (c->fixed_point) s.fftEngine = FFTEngine::KISS;
 
         h->fg = std::make_unique<Flowgraph>(false);
         h->input = std::make_shared<BitsInput>();

@@ -42,19 +42,22 @@ def test_adapter_library_links():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not have, reason="reference libraries not built")
-@pytest.mark.parametrize("case", ["c1", "c2", "c3", "tm2_s16_tii"])
+@pytest.mark.parametrize("case", ["c1", "c2", "c3", "tm2_s16_tii", "tm1_fixed", "tm4_fixed_window"])
 def test_adapter_in_reference_flowgraph(rng, tmp_path, case):
     L = adp()
     kw = {"c1": dict(mode=1), "c2": dict(mode=1, fir_taps_file="default"),
           "c3": dict(mode=1, fir_taps_file="default", output_rate=8192000, normalise=1.0 / 46000.0),
-          "tm2_s16_tii": dict(mode=2, tii=(3, 20, 0), digital_gain=0.8, fmt="s16")}[case]
+          "tm2_s16_tii": dict(mode=2, tii=(3, 20, 0), digital_gain=0.8, fmt="s16"),
+          "tm1_fixed": dict(mode=1, fixed_point=True, tii=(5, 8, 0)),
+          "tm4_fixed_window": dict(mode=4, fixed_point=True, window_overlap=20)}[case]
+    fixed = bool(kw.get("fixed_point"))
     if case == "c3":
         p = str(tmp_path / "poly.coef")
         write_poly_file(p, [1.0, 0.05, -0.02, 0.0, 0.0], [0.0, 0.1, -0.05, 0.0, 0.0])
         kw["poly_coef_file"] = p
         kw["poly_threads"] = 1
     mode = kw["mode"]
-    dt = np.int16 if kw.get("fmt") == "s16" else np.complex64
+    dt = np.int16 if kw.get("fmt") == "s16" or fixed else np.complex64
     bits = rng.integers(0, 256, (3, refwrap.TF_BYTES[mode]), dtype=np.uint8)
     ref = refwrap.RefChain(**kw)
     want = ref.run(bits, dtype=dt)
@@ -66,13 +69,19 @@ def test_adapter_in_reference_flowgraph(rng, tmp_path, case):
         assert n > 0, L.adp_last_error().decode()      # no priming latency: every call returns its TF
         got = out[:n].view(dt)
         assert got.size == want[i].size
-        if dt is np.int16:
+        if fixed:
+            assert np.array_equal(got, want[i])          # the fixed-point engine is bit-exact
+        elif dt is np.int16:
             d = np.abs(got.astype(np.int32) - want[i].astype(np.int32))
             assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size
         else:
             assert rel_rms(got, want[i]) < TOL
     # wrong input size throws inside process() like the reference blocks do -> harness reports -1
     assert L.adp_process(h, bits[0].ctypes.data, 100, out.ctypes.data, out.size) == -1
+    if fixed:
+        assert L.adp_set_parameter(h, b"digital", b"0.5") == -1      # no GainControl in the fixed-point chain
+        L.adp_destroy(h)
+        return
     # remote control through the RemoteControllable interface
     assert L.adp_set_parameter(h, b"digital", b"0.5") == 0
     buf = ctypes.create_string_buffer(64)
