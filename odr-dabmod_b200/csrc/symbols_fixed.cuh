@@ -58,7 +58,7 @@ struct FixParams {
 
 struct FixSmem {
     uint32_t buf[FX_BUF];         // int16 pairs, fxpad layout
-    short2 tw[FX_POINTS];
+    uint32_t tw[FX_POINTS];       // kiss twiddles, int16 pairs
     uint32_t spread[256];
     short2 c8[8];
     short2 tail[FX_MAX_WINDOW];   // falling edge of the last symbol of the previous group
@@ -79,7 +79,12 @@ __device__ __forceinline__ short fx_mul(short a, short b)
 // results of in-range operands fit an int16 by construction (|x| <= 32767 -> |x * 8191 >> 15| <= 8192,
 // twiddles <= 32767), so they need no reduction either.
 struct fxc { int x, y; };
-__device__ __forceinline__ fxc fx_unpack(uint32_t w) { return fxc{(int)(w << 16) >> 16, (int)w >> 16}; }
+__device__ __forceinline__ fxc fx_unpack(uint32_t w)
+{
+    int lo;     // prmt in its default mode: selector nibble 9 = sign of byte 1 replicated (the low half, sign extended)
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(lo) : "r"(w));
+    return fxc{lo, (int)w >> 16};
+}
 __device__ __forceinline__ uint32_t fx_pack(fxc c) { return __byte_perm((uint32_t)c.x, (uint32_t)c.y, 0x5410); }
 __device__ __forceinline__ int fx_sround(int x) { return (x + (1 << 14)) >> 15; }
 __device__ __forceinline__ fxc fx_fixdiv(fxc c, int k)              // C_FIXDIV: k = 32767 / radix
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
     const int W = p.window;
 
     // ---- per-CTA tables ----
-    for (int i = tid; i < N; i += FX_THREADS) sm.tw[i] = __ldg(p.tw + i);
+    for (int i = tid; i < N; i += FX_THREADS) sm.tw[i] = __ldg(reinterpret_cast<const uint32_t *>(p.tw) + i);
     for (int b = tid; b < 256; b += FX_THREADS) {
         uint32_t s = 0;
 #pragma unroll
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
         __syncthreads();
 
         // ---- 2. KISS inverse FFT, in place, smallest sub-transforms first ----
-        fx_ifft<N>(sm.buf, reinterpret_cast<const uint32_t *>(sm.tw), tid);
+        fx_ifft<N>(sm.buf, sm.tw, tid);
 
         // ---- 3. guard interval (+ window) and store ----
         for (int g = 0; g < G; g++) {
@@ -333,6 +338,19 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
             if (s > p.L) break;
             const int x0 = g * N;
             const int size = fx_size(p, s), pre = size - N, pos = fx_pos(p, s);
+            if (W == 0) {
+                // plain guard interval: cyclic prefix + body, VEC samples per access (the symbol sizes of the
+                // mode are multiples of VEC, so a vector never wraps and stays aligned; fxpad keeps runs of 8)
+                constexpr int VEC = (N == 2048 || N == 1024) ? 4 : N == 512 ? 2 : 1;
+                for (int o = VEC * tid; o < size; o += VEC * FX_THREADS) {
+                    const uint32_t *src = sm.buf + fxpad(x0 + ((o - pre) & (N - 1)));
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(out + pos + o);
+                    if (VEC == 4) *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
+                    else if (VEC == 2) *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(src);
+                    else *dst = *src;
+                }
+                continue;
+            }
             const bool first = s == 0, last = s == p.L;
             const int lo = (W > 0 && !first) ? -W : 0;
             const int hi = (W > 0 && !last) ? size - W : size;
