@@ -41,6 +41,9 @@ TF_SAMPLES = 196608
 # algorithmic bytes per TM I TF
 SYM_BYTES_PER_TF = TF_IN_BYTES + TF_SAMPLES * 8          # 1 601 664
 FIR_BYTES_PER_TF = 2 * TF_SAMPLES * 8                    # 3 145 728
+# k_fir_sym reads the symbol kernel's compact layout (76 symbols x 2048 samples)
+COMPACT_SAMPLES = 76 * 2048                              # 155 648
+FIR_SYM_BYTES_PER_TF = (COMPACT_SAMPLES + TF_SAMPLES) * 8   # 2 818 048
 METRIC = "ETI frames/sec (TM I, 2.048 Msps I/Q) at 1/2/4/8 B200 vs reference CPU"
 WORKLOAD = "TM I, batched 1024 frames on 1xB200, native rate, FIRFilter enabled (default taps)"
 
@@ -491,7 +494,10 @@ def gpu_arm(args):
 
     peak, peak_src = measured_peaks()
     bytes_per_launch = {"k_symbols": SYM_BYTES_PER_TF * n_tf, "k_symbols_w": SYM_BYTES_PER_TF * n_tf,
-                        "k_fir": FIR_BYTES_PER_TF * n_tf}
+                        "k_fir": FIR_BYTES_PER_TF * n_tf, "k_fir_sym": FIR_SYM_BYTES_PER_TF * n_tf}
+    if "k_fir_sym" in kavg:
+        # compact intermediate: the symbol kernel writes 76 x 2048 samples per TF (no null symbol, no cyclic prefix)
+        bytes_per_launch["k_symbols_w"] = (TF_IN_BYTES + COMPACT_SAMPLES * 8) * n_tf
     dom = max(kavg, key=lambda k: kavg[k])
     achieved = bytes_per_launch[dom] / (kavg[dom] * 1e-3) / 1e9
     roofline = {

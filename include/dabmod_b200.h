@@ -151,7 +151,8 @@ int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits
  *   "enable", "comb", "pattern", "old_variant"  TII.cpp:339-376 (prefixed "tii." here)
  * plus "taps" (count, then taps, whitespace separated: FIRFilter tapsfile
  * content) and "coefs" (MemlessPoly coefficient-file content).
- * Not in the reference: "profile" (0|1, see dabmod_b200_kernel_time) and
+ * Not in the reference: "profile" (0|1, see dabmod_b200_kernel_time), the kernel selection knobs
+ * "sym_kernel" / "fir_kernel" / "res_kernel" (0 = always the general kernel; they never change results) and
  * "sym_chunks" (CTAs per TF of the symbol kernel, 0 = automatic; a tuning knob
  * that never changes results).
  * Takes effect at the next process call. */

@@ -200,6 +200,7 @@ struct dabmod_b200 {
     DevBuf<float> d_twiddle;       // interleaved re/im, per-pass tables (symbol_fft_twiddles)
     DevBuf<float> d_twiddle_w;     // second-pass table of k_symbols_w (TM I only)
     bool use_warp_kernel = true;   // "sym_kernel" knob: 0 = always the CTA-per-symbol-group kernel
+    bool use_fir_sym = true;       // "fir_kernel" knob: 0 = always the sample-stream FIR kernel
     int n_twiddle = 0;
     DevBuf<uint16_t> d_tii_bin;
     DevBuf<float> d_tii_val;
@@ -548,10 +549,15 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     sp.post = make_post(h, sym_post);
 
     const bool sym_opt = c.cfr_enable != 0 || c.window_overlap > 0;
+    const bool warp_kernel = m.N == SW_N && h->use_warp_kernel && !sym_opt && !h->use_cic && h->tii_count == 0;
+    // ... followed by the default-length FIR: the symbol kernel leaves out null symbol and cyclic prefix,
+    // k_fir_sym works symbol by symbol on that compact layout (kernels.cuh)
+    const bool compact = warp_kernel && fir && h->fir_taps.size() == 45 && h->use_fir_sym;
     // TM I without the optional per-carrier features: one warp per symbol (symbols_warp.cuh)
-    if (m.N == SW_N && h->use_warp_kernel && !sym_opt && !h->use_cic && h->tii_count == 0) {
+    if (warp_kernel) {
         SymWParams wp{};
         wp.s = sp;
+        wp.compact = compact ? 1 : 0;
         wp.twiddle_w = reinterpret_cast<const float2 *>(h->d_twiddle_w.p);
         wp.n_tf = (int)n_tf;
         // persistent: one CTA per SM, every warp takes one contiguous range of the batch's symbols
@@ -586,7 +592,23 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     launches++;
     }
 
-    if (fir) {
+    if (fir && compact) {
+        FirSymParams fp{};
+        fp.in = reinterpret_cast<const float2 *>(sp.out);
+        fp.out = dst;
+        fp.L = m.L; fp.null_size = m.null_size; fp.sym_size = m.sym_size; fp.tf_samples = m.tf_samples;
+        std::memset(fp.taps, 0, sizeof(fp.taps));
+        for (size_t j = 0; j < h->fir_taps.size(); j++) fp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
+        fp.post = make_post(h, post);
+        const int fgrid = (int)(n_tf * m.L);
+        ProfScope prof_fir(h, "k_fir_sym", s);
+        if (post) k_fir_sym<45, true><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
+        else k_fir_sym<45, false><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
+        CUDA_CHECK(cudaGetLastError());
+        prof_fir.end();
+        launches++;
+    }
+    else if (fir) {
         FirParams fp{};
         fp.in = reinterpret_cast<const float2 *>(sp.out);
         fp.out = dst;
@@ -1175,6 +1197,7 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             else if (n == "profile") { int v; ss >> v; h->profile = v != 0; }
             else if (n == "sym_chunks") { int v; ss >> v; h->force_chunks = v < 0 ? 0 : v; }
             else if (n == "sym_kernel") { int v; ss >> v; h->use_warp_kernel = v != 0; }
+            else if (n == "fir_kernel") { int v; ss >> v; h->use_fir_sym = v != 0; }
             else if (n == "res_kernel") { int v; ss >> v; h->allow_res_up = v != 0; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {

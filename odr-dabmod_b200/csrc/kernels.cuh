@@ -864,6 +864,154 @@ __global__ void __launch_bounds__(FIR_THREADS) k_fir(const __grid_constant__ Fir
 }
 
 // ---------------------------------------------------------------------------
+// k_fir_sym: the same filter for TM I fed by k_symbols_w in its compact layout
+// ([tf][symbol 1..L][N] samples, no null symbol, no cyclic prefix).  One CTA = one
+// OFDM symbol.  Two facts about the guard-interval stream make this cheaper than
+// filtering it sample by sample, with bit-identical results:
+//   * the cyclic prefix is a copy of the symbol's tail and the filter is shift
+//     invariant, so the outputs over the prefix, except the last NT-1, ARE the
+//     outputs over the tail (same operands, same order): 460 of a symbol's 2552
+//     outputs are copies, not computed (-17 % multiply-adds);
+//   * the prefix need not exist in memory: the filter input is N samples per
+//     symbol instead of sym_size (-21 % reads), and the symbol kernel writes 21 % less.
+// Per symbol: N outputs over the body (window reaching into the next symbol's prefix
+// = that symbol's samples N-pre ...), NT-1 outputs across the prefix/body seam
+// (a circular window), and for symbol 1 the NT-1 outputs at the end of the null
+// symbol.  Zeros (null symbol, beyond the TF end) enter as 0 * tap like in k_fir.
+// ---------------------------------------------------------------------------
+struct FirSymParams {
+    const float2 *in;     // n_tf * L * N samples, compact
+    void *out;            // n_tf * tf_samples
+    int L, null_size, sym_size, tf_samples;
+    float2 taps[MAX_FIR_TAPS];
+    PostParams post;
+};
+
+constexpr int FIRS_THREADS = FIR_THREADS + 32;   // four warps on the body, one on the seams
+constexpr int FIRS_SM = 4;                        // seam outputs per lane of the fifth warp
+
+template <int NT, bool POST>
+__global__ void __launch_bounds__(FIRS_THREADS, 8) k_fir_sym(const __grid_constant__ FirSymParams p)
+{
+    constexpr int N = FIR_TILE;                 // 2048 = TM I spacing
+    constexpr int H = NT - 1;                   // halo
+    constexpr int XS_IN = N + NT + (N + NT) / 16 + 8;
+    constexpr int XS_OUT = FIR_THREADS * (FIR_M + 2);        // padded output staging (float4 slots 9*t)
+    constexpr int SEAM_LANES = (H + FIRS_SM - 1) / FIRS_SM;  // 11 lanes x 4 outputs per seam
+    static_assert(2 * SEAM_LANES <= 32 && SEAM_LANES <= 16, "the seams are one warp's work");
+    // body + next symbol's prefix head (fpad layout); later the transposed staging of the body outputs
+    __shared__ __align__(16) float2 xs[XS_IN > XS_OUT ? XS_IN : XS_OUT];
+    __shared__ float2 seam[2][SEAM_LANES * FIRS_SM];         // outputs of the two seams
+    const int tid = threadIdx.x;
+    const int tf = blockIdx.x / p.L;
+    const int s = 1 + (blockIdx.x - tf * p.L);               // symbol 1..L
+    const int pre = p.sym_size - N;                          // cyclic prefix length
+    const float2 *body = p.in + ((size_t)tf * p.L + (s - 1)) * N;
+    const bool has_next = s < p.L;
+
+    // stage the head of the next symbol's prefix (zeros beyond the TF; fetched first so that its latency
+    // overlaps the body's) and the body
+    float2 halo = make_float2(0.f, 0.f);
+    if (has_next && tid < H) halo = __ldg(body + N + (N - pre) + tid);
+    {
+        // all loads in flight before the first shared store (a rolled loop would serialise the round trips)
+        constexpr int NLD = (N / 2 + FIRS_THREADS - 1) / FIRS_THREADS;
+        float4 v[NLD];
+#pragma unroll
+        for (int k = 0; k < NLD; k++) {
+            const int i = 2 * (tid + k * FIRS_THREADS);
+            v[k] = i < N ? __ldg(reinterpret_cast<const float4 *>(body + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < NLD; k++) {
+            const int i = 2 * (tid + k * FIRS_THREADS);
+            if (i < N) {
+                xs[fpad(i)] = make_float2(v[k].x, v[k].y);
+                xs[fpad(i + 1)] = make_float2(v[k].z, v[k].w);
+            }
+        }
+    }
+    if (tid < NT) xs[fpad(N + tid)] = halo;
+    __syncthreads();
+
+    float2 acc[FIR_M];
+#pragma unroll
+    for (int m = 0; m < FIR_M; m++) acc[m] = make_float2(0.f, 0.f);
+    if (tid < FIR_THREADS) {
+        const float2 *x = xs + tid * (FIR_M + 1);            // fpad(tid * FIR_M)
+#pragma unroll
+        for (int i = 0; i < FIR_M + NT - 1; i++) {
+            const float2 v = x[i + (i >> 4)];
+#pragma unroll
+            for (int m = 0; m < FIR_M; m++) {
+                const int j = i - m;
+                if (j >= 0 && j < NT) acc[m] = __ffma2_rn(v, p.taps[j], acc[m]);
+            }
+        }
+    }
+    else {
+        // The seams, ascending tap order like everything else, zeros entering as 0 * tap like in k_fir:
+        //   lanes 0-10:  the last NT-1 prefix positions -- window over the prefix end (= body end), then the body start;
+        //   lanes 16-26 (symbol 1): the last NT-1 positions of the null symbol -- zeros, then the prefix start.
+        const int lane = tid - FIR_THREADS, which = lane >> 4, l = lane & 15;
+        if (l < SEAM_LANES && (which == 0 || s == 1)) {
+            const int i0 = FIRS_SM * l;
+#pragma unroll
+            for (int i = 0; i < FIRS_SM + NT - 1; i++) {
+                const int t = i0 + i;                        // position in the seam's 2H-sample input
+                float2 v = make_float2(0.f, 0.f);
+                if (which == 0) v = xs[fpad(t < H ? N - H + t : t - H)];
+                else if (t >= H) v = xs[fpad(N - pre + t - H)];
+#pragma unroll
+                for (int m = 0; m < FIRS_SM; m++) {
+                    const int j = i - m;
+                    if (j >= 0 && j < NT) acc[m] = __ffma2_rn(v, p.taps[j], acc[m]);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < FIRS_SM; m++) seam[which][i0 + m] = acc[m];
+        }
+    }
+    __syncthreads();                                         // everybody is done with xs
+    float4 *ys = reinterpret_cast<float4 *>(xs);
+    if (tid < FIR_THREADS) {
+#pragma unroll
+        for (int m = 0; m < FIR_M; m += 2)
+            ys[tid * (FIR_M / 2 + 1) + m / 2] = make_float4(acc[m].x, acc[m].y, acc[m + 1].x, acc[m + 1].y);
+    }
+    __syncthreads();
+
+    // ---- store: [null symbol (s == 1)] | prefix | body, coalesced pairs ----
+    unsigned clip = 0;
+    const size_t tf_base = (size_t)tf * p.tf_samples;
+    const size_t pos = tf_base + p.null_size + (size_t)(s - 1) * p.sym_size;
+    const float2 *yb = reinterpret_cast<const float2 *>(ys);
+    auto body_out = [&](int n) {                             // output over body sample n
+        const int q = n >> 1;
+        return yb[2 * (q + (q >> 3)) + (n & 1)];
+    };
+    for (int q = tid; q < N / 2; q += FIRS_THREADS) {        // body
+        const float4 v = ys[q + (q >> 3)];
+        if (!POST) reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + pos + pre)[q] = v;
+        else {
+            store_sample<POST>(p.out, pos + pre + 2 * q, make_float2(v.x, v.y), p.post, clip);
+            store_sample<POST>(p.out, pos + pre + 2 * q + 1, make_float2(v.z, v.w), p.post, clip);
+        }
+    }
+    for (int o = tid; o < pre; o += FIRS_THREADS) {          // prefix: copies of the tail outputs, then the seam
+        const float2 v = o < pre - H ? body_out(N - pre + o) : seam[0][o - (pre - H)];
+        store_sample<POST>(p.out, pos + o, v, p.post, clip);
+    }
+    if (s == 1) {                                            // null symbol: zeros, then its seam with symbol 1
+        for (int o = tid; o < p.null_size; o += FIRS_THREADS) {
+            const float2 v = o < p.null_size - H ? make_float2(0.f, 0.f) : seam[1][o - (p.null_size - H)];
+            store_sample<POST>(p.out, tf_base + o, v, p.post, clip);
+        }
+    }
+    if (POST && p.post.format != 0) flush_clip(p.post, clip);
+}
+
+// ---------------------------------------------------------------------------
 // k_post: stand-alone [MemlessPoly] -> [FormatConverter] for chains where no
 // other kernel can carry the epilogue.  Reference: see PostParams.
 // ---------------------------------------------------------------------------

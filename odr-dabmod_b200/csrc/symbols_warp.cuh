@@ -53,6 +53,9 @@ struct SymWParams {
     SymParams s;                            // shared with k_symbols
     const float2 *twiddle_w;                // 31 * 64 entries
     int n_tf;
+    int compact;                            // 1: write only the N samples of every data symbol, back to back
+                                            // ([tf][s-1][N], no null symbol, no cyclic prefix): the layout
+                                            // k_fir_sym reads (it rebuilds the guard interval itself)
 };
 
 // I/Q bit bytes of the lane's 48 carriers in one bit row: 6 bytes each, as (4 bytes, 2 bytes)
@@ -222,8 +225,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                 // start of a TF.  Null symbol without TII: all-zero carriers -> all-zero samples,
                 // whatever gain it borrows from symbol 1 (GainControl.cpp:139-144).  The
                 // differential chain restarts from the phase reference (DifferentialModulator.cpp:65).
-                for (int i = lane; i < p.null_size; i += 32)
-                    store_sample<POST>(p.out, out_base + i, make_float2(0.f, 0.f), p.post, clip);
+                if (!pw.compact) {
+                    for (int i = lane; i < p.null_size; i += 32)
+                        store_sample<POST>(p.out, out_base + i, make_float2(0.f, 0.f), p.post, clip);
+                }
 #pragma unroll
                 for (int w = 0; w < 6; w++) ph[w] = sm.ph0[w * 32 + lane];
             }
@@ -371,9 +376,15 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        float2 *gout = reinterpret_cast<float2 *>(p.out) + pos;
-                        sw_bulk_store(gout + pre, xb, N * (int)sizeof(float2));
-                        sw_bulk_store(gout, xb + (N - pre), pre * (int)sizeof(float2));
+                        if (pw.compact) {
+                            float2 *gout = reinterpret_cast<float2 *>(p.out) + ((size_t)tf * L + (s - 1)) * N;
+                            sw_bulk_store(gout, xb, N * (int)sizeof(float2));
+                        }
+                        else {
+                            float2 *gout = reinterpret_cast<float2 *>(p.out) + pos;
+                            sw_bulk_store(gout + pre, xb, N * (int)sizeof(float2));
+                            sw_bulk_store(gout, xb + (N - pre), pre * (int)sizeof(float2));
+                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }

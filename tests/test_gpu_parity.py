@@ -68,6 +68,36 @@ def test_fir_default_taps(dm, rng, mode):
     assert mod.last_launch_count == 2
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(fmt="s16", digital_gain=0.7), dict(gain_mode="max"),
+                                dict(output_rate=4096000), dict(poly=[1.0, 0.05, -0.02, 0.003, 0.0, 0.0, 0.1, -0.05, 0.01, 0.0],
+                                                                normalise=1.0 / 46000.0)],
+                         ids=["complexf", "s16", "gain_max", "resampler_after", "poly"])
+def test_fir_symbol_kernel(dm, rng, kw):
+    """k_fir_sym (TM I, default taps, symbol kernel in its compact layout: the cyclic-prefix outputs are copies of the
+    tail outputs, the prefix itself is never stored) produces the same BITS as the sample-stream k_fir, and both
+    agree with the oracle."""
+    bits = bits_for(rng, 1, 3)
+    taps = oracle.fir_default_taps()
+    a = dm.Modulator(mode=1, fir_taps=taps, max_batch=3, **kw)
+    a.set_param("profile", 1)
+    ya = a.process_batch(bits)
+    assert "k_fir_sym" in [k for k, _ in a.kernel_times()]
+    b = dm.Modulator(mode=1, fir_taps=taps, max_batch=3, **kw)
+    b.set_param("fir_kernel", 0)
+    b.set_param("profile", 1)
+    yb = b.process_batch(bits)
+    assert "k_fir" in [k for k, _ in b.kernel_times()]
+    assert ya.dtype == yb.dtype and np.array_equal(ya.view(np.uint8), yb.view(np.uint8))
+    if "fmt" not in kw:
+        want = oracle.OracleChain(mode=1, fir_taps=taps, **kw).run(bits)
+        for i in range(3):
+            assert rel_rms(ya[i], want[i]) < TOL, i
+    # one TF at a time gives the same bits again (the last symbol's window ends in zeros, not in the next TF)
+    a.reset()
+    for i in range(3):
+        assert np.array_equal(a.process(bits[i]).view(np.uint8), ya[i].view(np.uint8)), i
+
+
 @pytest.mark.parametrize("ntaps", [1, 2, 16, 17, 33, 64, 97, 128])
 def test_fir_tap_counts(dm, rng, ntaps):
     bits = bits_for(rng, 2, 1)
