@@ -600,7 +600,7 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         std::memset(fp.taps, 0, sizeof(fp.taps));
         for (size_t j = 0; j < h->fir_taps.size(); j++) fp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
         fp.post = make_post(h, post);
-        const int fgrid = (int)(n_tf * m.L);
+        const dim3 fgrid((unsigned)m.L, (unsigned)n_tf);
         ProfScope prof_fir(h, "k_fir_sym", s);
         if (post) k_fir_sym<45, true><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
         else k_fir_sym<45, false><<<fgrid, FIRS_THREADS, 0, s>>>(fp);

@@ -901,10 +901,10 @@ __global__ void __launch_bounds__(FIRS_THREADS, 8) k_fir_sym(const __grid_consta
     static_assert(2 * SEAM_LANES <= 32 && SEAM_LANES <= 16, "the seams are one warp's work");
     // body + next symbol's prefix head (fpad layout); later the transposed staging of the body outputs
     __shared__ __align__(16) float2 xs[XS_IN > XS_OUT ? XS_IN : XS_OUT];
-    __shared__ float2 seam[2][SEAM_LANES * FIRS_SM];         // outputs of the two seams
+    __shared__ __align__(16) float2 seam[2][SEAM_LANES * FIRS_SM];   // outputs of the two seams
     const int tid = threadIdx.x;
-    const int tf = blockIdx.x / p.L;
-    const int s = 1 + (blockIdx.x - tf * p.L);               // symbol 1..L
+    const int tf = blockIdx.y;                               // grid: (L, n_tf)
+    const int s = 1 + blockIdx.x;                            // symbol 1..L
     const int pre = p.sym_size - N;                          // cyclic prefix length
     const float2 *body = p.in + ((size_t)tf * p.L + (s - 1)) * N;
     const bool has_next = s < p.L;
@@ -985,28 +985,25 @@ __global__ void __launch_bounds__(FIRS_THREADS, 8) k_fir_sym(const __grid_consta
     unsigned clip = 0;
     const size_t tf_base = (size_t)tf * p.tf_samples;
     const size_t pos = tf_base + p.null_size + (size_t)(s - 1) * p.sym_size;
-    const float2 *yb = reinterpret_cast<const float2 *>(ys);
-    auto body_out = [&](int n) {                             // output over body sample n
-        const int q = n >> 1;
-        return yb[2 * (q + (q >> 3)) + (n & 1)];
-    };
-    for (int q = tid; q < N / 2; q += FIRS_THREADS) {        // body
-        const float4 v = ys[q + (q >> 3)];
-        if (!POST) reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + pos + pre)[q] = v;
+    auto emit2 = [&](size_t at, float4 v) {                  // two samples at an even position
+        if (!POST) *reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + at) = v;
         else {
-            store_sample<POST>(p.out, pos + pre + 2 * q, make_float2(v.x, v.y), p.post, clip);
-            store_sample<POST>(p.out, pos + pre + 2 * q + 1, make_float2(v.z, v.w), p.post, clip);
+            store_sample<POST>(p.out, at, make_float2(v.x, v.y), p.post, clip);
+            store_sample<POST>(p.out, at + 1, make_float2(v.z, v.w), p.post, clip);
         }
-    }
-    for (int o = tid; o < pre; o += FIRS_THREADS) {          // prefix: copies of the tail outputs, then the seam
-        const float2 v = o < pre - H ? body_out(N - pre + o) : seam[0][o - (pre - H)];
-        store_sample<POST>(p.out, pos + o, v, p.post, clip);
+    };
+    for (int q = tid; q < N / 2; q += FIRS_THREADS) emit2(pos + pre + 2 * q, ys[q + (q >> 3)]);      // body
+    // prefix: copies of the outputs over the tail (pairs stay aligned: N - pre, pre and H are even), then the seam
+    const float4 *seam4 = reinterpret_cast<const float4 *>(seam[0]);
+    for (int q = tid; q < pre / 2; q += FIRS_THREADS) {
+        const int qb = (N - pre) / 2 + q;
+        emit2(pos + 2 * q, q < (pre - H) / 2 ? ys[qb + (qb >> 3)] : seam4[q - (pre - H) / 2]);
     }
     if (s == 1) {                                            // null symbol: zeros, then its seam with symbol 1
-        for (int o = tid; o < p.null_size; o += FIRS_THREADS) {
-            const float2 v = o < p.null_size - H ? make_float2(0.f, 0.f) : seam[1][o - (p.null_size - H)];
-            store_sample<POST>(p.out, tf_base + o, v, p.post, clip);
-        }
+        const float4 *seam4n = reinterpret_cast<const float4 *>(seam[1]);
+        for (int q = tid; q < p.null_size / 2; q += FIRS_THREADS)
+            emit2(tf_base + 2 * q, q < (p.null_size - H) / 2 ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                                             : seam4n[q - (p.null_size - H) / 2]);
     }
     if (POST && p.post.format != 0) flush_clip(p.post, clip);
 }
