@@ -516,7 +516,7 @@ def gpu_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = host_cores()
-        tfs = 96
+        tfs = 192
         v, dt_cpu, kind = run_cpu(cores, tfs)
         cpu = {"value": v, "unit": "ETI frames/s", "cores": cores, "kind": kind,
                "sample": "%d TFs per thread x %d threads, %.1f s (same TM I + FIR default taps chain)" % (tfs, cores, dt_cpu)}
