@@ -364,6 +364,8 @@ def measure_e2e_s16(dm, torch, host_bits, n_tf, steps=5):
 def bind_to_gpu_numa_node(gpu_index):
     """Run this rank (and allocate its pinned host buffers) on the CPUs next to its GPU: the end-to-end leg
     moves 1.6 GB per step over PCIe, and a remote NUMA node costs a third of that bandwidth."""
+    if os.environ.get("DABMOD_BENCH_NO_BIND"):
+        return
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -545,7 +547,7 @@ def gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "mode": MODE, "tfs_per_step_per_gpu": n_tf,
                    "eti_frames_per_step": eti_per_step, "output": "complexf", "gain": "var",
-                   "l2": "per-step working set 3.2 GB (1.6 GB symbol-stage + 1.6 GB output) >> 126 MB L2; "
+                   "l2": "per-step working set 2.9 GB (1.3 GB symbol-stage, compact layout + 1.6 GB output) >> 126 MB L2; "
                          "input bits rotate over 4 buffers",
                    "parallelism": "frame-sharded x%d, no collective" % world},
         "e2e": {"value": e2e_value, "unit": "ETI frames/s", "h2d_bytes_per_step": in_bytes,
