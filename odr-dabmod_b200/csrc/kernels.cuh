@@ -273,7 +273,7 @@ __device__ __forceinline__ void sym_fft(float2 *buf, const float2 *tw, int tid)
 // reduction (OfdmGenerator.cpp:310-373) and OFDM windowing (GuardIntervalInserter.cpp:149-300).
 // They cost shared memory and registers, so the plain configurations get their own instantiation.
 template <int N, bool POST, bool OPT>
-__global__ void __launch_bounds__(SYM_THREADS) k_symbols(const __grid_constant__ SymParams p)
+__global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __grid_constant__ SymParams p)
 {
     constexpr int G = SYM_POINTS / N;         // symbols per group
     constexpr int TG = SYM_THREADS / G;       // threads per symbol in the emit phase

@@ -18,13 +18,13 @@ ncu --set full --clock-control none --import-source on -k regex:k_fir -s 2 -c 1 
 bash tools/prof_kernel.sh k_resample_q c5 resq_$TAG
 bash tools/prof_kernel.sh k_resample_up "c3 " resup_$TAG
 bash tools/prof_kernel.sh k_symbols_fix n4 fix_$TAG
-bash tools/prof_kernel.sh "k_symbols<" "c4 TM II" sym2_$TAG
+bash tools/prof_kernel.sh "^k_symbols$" "c4 TM IV" sym4_$TAG
 SUM=gpurun_out/ncu_summary_$TAG.txt
 : > $SUM
-for r in symbols fir resq resup fix sym2; do
+for r in symbols fir resq resup fix sym4; do
   python tools/ncu_summary.py gpurun_out/prof_${r}_$TAG.ncu-rep >> $SUM
   python tools/ncu_summary.py gpurun_out/prof_${r}_$TAG.ncu-rep --all | grep -E "average_warps_issue_stalled" >> $SUM
 done
-rm -f gpurun_out/prof_resq_$TAG.ncu-rep gpurun_out/prof_resup_$TAG.ncu-rep gpurun_out/prof_fix_$TAG.ncu-rep gpurun_out/prof_sym2_$TAG.ncu-rep
+rm -f gpurun_out/prof_resq_$TAG.ncu-rep gpurun_out/prof_resup_$TAG.ncu-rep gpurun_out/prof_fix_$TAG.ncu-rep gpurun_out/prof_sym4_$TAG.ncu-rep
 ls -la gpurun_out | tail -12
 fi
