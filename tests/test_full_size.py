@@ -1,0 +1,105 @@
+"""BASELINE.json's full batch sizes on the GPU, checked through size-independent properties (the oracle needs
+~10 ms per TF, so only sampled frames are compared with it):
+
+  * a frame of a big batch equals the same frame processed alone, bit for bit (frames are independent except for
+    the resampler history and the TII toggle, both functions of the stream position);
+  * the host-buffer entry point (sliced three-stream pipeline) and the device-buffer entry point agree bit for bit;
+  * the FIR is linear in its taps (a power-of-two scale is exact in float32);
+  * a batch equals the same stream cut into several calls (resampler history across calls).
+"""
+import numpy as np
+import pytest
+
+import dabmod_loader
+from conftest import rel_rms
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def dm():
+    return dabmod_loader.load()
+
+
+def test_config2_full_batch(dm):
+    """configs[1]: TM I, 1024 frames in one call, FIR default taps (k_symbols_w compact + k_fir_sym)."""
+    import torch
+    n = 1024
+    rng = np.random.default_rng(2024)
+    m = oracle.mode_params(1)
+    bits = rng.integers(0, 256, (n, m.tf_bytes), dtype=np.uint8)
+    taps = oracle.fir_default_taps()
+    mod = dm.Modulator(mode=1, fir_taps=taps, max_batch=n)
+    out = mod.process_batch(bits)
+    assert out.shape == (n, m.tf_samples)
+    # sampled frames: alone == in the batch, and against the oracle
+    one = dm.Modulator(mode=1, fir_taps=taps, max_batch=1)
+    for i in (0, 1, 31, 32, 511, 1023):                      # 31 | 32: a slice boundary of the host pipeline
+        assert np.array_equal(one.process(bits[i]).view(np.uint32), out[i].view(np.uint32)), i
+    ora = oracle.OracleChain(mode=1, fir_taps=taps)
+    for i in (0, 1023):
+        assert rel_rms(out[i], ora.process(bits[i])) < TOL, i
+    # device entry point: same bits as the host pipeline (whole batch, word for word)
+    d_in = torch.from_numpy(bits).cuda()
+    d_out = torch.empty(n * mod.tf_out_bytes, dtype=torch.uint8, device="cuda")
+    mod.process_batch_device(d_in.data_ptr(), n, d_out.data_ptr())
+    mod.synchronize()
+    dev = d_out.view(torch.int32)
+    host = torch.from_numpy(out.view(np.int32).reshape(-1)).cuda()
+    assert bool(torch.equal(dev, host))
+    # gain var: every frame's symbols are scaled to the same spread (GainControl.cpp:251-340), null symbol silent
+    x = d_out.view(torch.float32).view(n, -1, 2)
+    assert float(x[:, :2600].abs().max()) == 0.0
+    p = (x[:, 4000:] ** 2).sum(dim=(1, 2)) / (x.shape[1] - 4000)
+    assert float(p.max() / p.min()) < 1.05       # the gain follows max(sigma_re, sigma_im), not the total power
+    # linearity in the taps: 2 * taps -> exactly 2 * output
+    mod2 = dm.Modulator(mode=1, fir_taps=[2.0 * t for t in taps], max_batch=n)
+    mod2.process_batch_device(d_in.data_ptr(), n, d_out.data_ptr())
+    mod2.synchronize()
+    assert bool(torch.equal(d_out.view(torch.float32), 2.0 * host.view(torch.float32)))
+
+
+def test_fixed_point_full_batch(dm):
+    """Row N4 at 1024 frames with TII: bit-exact, the TII symbol on every second frame of the stream."""
+    n = 1024
+    rng = np.random.default_rng(2025)
+    m = oracle.mode_params(1)
+    bits = rng.integers(0, 256, (n, m.tf_bytes), dtype=np.uint8)
+    mod = dm.Modulator(mode=1, fixed_point=True, tii=(7, 21, 0), max_batch=n)
+    out = mod.process_batch(bits)
+    ora = oracle.OracleChain(mode=1, fixed_point=True, tii=(7, 21, 0))
+    for i in range(4):                                       # the oracle walks the stream from its start
+        assert np.array_equal(out[i], ora.process(bits[i])), i
+    one = dm.Modulator(mode=1, fixed_point=True, tii=(7, 21, 0), max_batch=1)
+    for i in (510, 511, 1022, 1023):
+        one.seek(i)
+        assert np.array_equal(one.process(bits[i]), out[i]), i
+    null = out[:, : 2 * 2656].astype(np.int32)
+    energy = (null ** 2).sum(axis=1)
+    assert (energy[0::2] > 0).all() and (energy[1::2] == 0).all()
+
+
+@pytest.mark.parametrize("rate", [10000000, 8192000])
+def test_config5_stream_in_pieces(dm, rate):
+    """configs[4] / [2] geometry: FIR + resampler + MemlessPoly; 96 frames in one call == the same stream in calls of
+    40 + 1 + 55 frames == a second handle that seeks to frame 41 (what a shard of the 8-GPU run does)."""
+    n = 96
+    rng = np.random.default_rng(2026)
+    m = oracle.mode_params(1)
+    bits = rng.integers(0, 256, (n, m.tf_bytes), dtype=np.uint8)
+    kw = dict(mode=1, output_rate=rate, normalise=1.0 / 46000.0, fir_taps=oracle.fir_default_taps(),
+              poly=[1.0, 0.05, -0.02, 0.003, 0.0, 0.0, 0.1, -0.05, 0.01, 0.0])
+    mod = dm.Modulator(max_batch=n, **kw)
+    whole = mod.process_batch(bits).copy()
+    mod.reset()
+    parts = np.concatenate([mod.process_batch(bits[:40]), mod.process_batch(bits[40:41]), mod.process_batch(bits[41:])])
+    assert np.array_equal(parts.view(np.uint32), whole.view(np.uint32))
+    shard = dm.Modulator(max_batch=n, **kw)
+    shard.seek(41, bits[40])
+    tail = shard.process_batch(bits[41:])
+    assert np.array_equal(tail.view(np.uint32), whole[41:].view(np.uint32))
+    ora = oracle.OracleChain(**kw)
+    for i in range(2):
+        assert rel_rms(whole[i], ora.process(bits[i])) < TOL, i
