@@ -39,7 +39,8 @@ enum {
     DABMOD_B200_ECUDA = -2,     /* CUDA runtime error, no usable device */
     DABMOD_B200_ENOMEM = -3,
     DABMOD_B200_EUNSUPPORTED = -4, /* valid for the reference, not implemented here */
-    DABMOD_B200_ESTATE = -5
+    DABMOD_B200_ESTATE = -5,
+    DABMOD_B200_EIO = -6           /* the output sink failed (write(2) error) */
 };
 
 /* GainMode, reference src/GainControl.h:45 */
@@ -121,6 +122,13 @@ int dabmod_b200_process(dabmod_b200 *h, const uint8_t *bits, size_t nbytes,
  * Copies are chunked and overlapped with the kernels on internal streams. */
 int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf,
                               void *iq_out, size_t cap, size_t *out_bytes);
+
+/* Same, delivered to a file descriptor instead of a buffer: what the reference's OutputFile node does with the
+ * chain's output (src/OutputFile.cpp:56-67, fwrite of every Buffer; "fileoutput" in the configuration).  The I/Q
+ * goes through a ring of pinned host buffers owned by the handle: slice i is written to `fd` while slice i+1 is
+ * on the PCIe link and slice i+2 in the kernels.  Short writes are completed, EINTR retried;
+ * any other write error returns DABMOD_B200_EIO (the reference throws).  *out_bytes = bytes written. */
+int dabmod_b200_process_batch_to_fd(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, int fd, size_t *out_bytes);
 
 /* Same, device-resident buffers on the handle's device; enqueued on `stream`
  * (a cudaStream_t, NULL = the handle's own stream) and NOT synchronised. */

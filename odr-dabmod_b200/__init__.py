@@ -29,7 +29,7 @@ EXPORTS = [
     "dabmod_b200_config_init", "dabmod_b200_default_fir_taps", "dabmod_b200_create",
     "dabmod_b200_destroy", "dabmod_b200_tf_in_bytes", "dabmod_b200_tf_out_bytes",
     "dabmod_b200_tf_out_samples", "dabmod_b200_process", "dabmod_b200_process_batch",
-    "dabmod_b200_process_batch_device", "dabmod_b200_synchronize", "dabmod_b200_reset",
+    "dabmod_b200_process_batch_device", "dabmod_b200_process_batch_to_fd", "dabmod_b200_synchronize", "dabmod_b200_reset",
     "dabmod_b200_seek", "dabmod_b200_set_param", "dabmod_b200_get_param",
     "dabmod_b200_num_clipped_samples", "dabmod_b200_last_launch_count", "dabmod_b200_last_error",
     "dabmod_b200_table_interleaver", "dabmod_b200_table_phase_ref", "dabmod_b200_table_tii",
@@ -120,6 +120,7 @@ def lib():
     L.dabmod_b200_process.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
     L.dabmod_b200_process_batch.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
     L.dabmod_b200_process_batch_device.argtypes = [vp, vp, sz, vp, vp]
+    L.dabmod_b200_process_batch_to_fd.argtypes = [vp, vp, sz, ctypes.c_int, ctypes.POINTER(sz)]
     L.dabmod_b200_synchronize.argtypes = [vp]
     L.dabmod_b200_reset.argtypes = [vp]
     L.dabmod_b200_seek.argtypes = [vp, ctypes.c_uint64, vp, sz]
@@ -300,6 +301,14 @@ class Modulator:
         return n.value
 
     # -- device buffers -----------------------------------------------------
+    def process_batch_to_fd(self, bits, fd):
+        """n_tf TFs of the stream written to the file descriptor `fd` (the reference's OutputFile sink) through the
+        handle's pinned ring; returns the number of bytes written."""
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(-1, self.tf_in_bytes)
+        n = ctypes.c_size_t(0)
+        _check(lib().dabmod_b200_process_batch_to_fd(self._h, bits.ctypes.data, bits.shape[0], fd, ctypes.byref(n)))
+        return n.value
+
     def process_batch_device(self, d_bits_ptr, n_tf, d_out_ptr, stream=0):
         _check(lib().dabmod_b200_process_batch_device(self._h, d_bits_ptr, n_tf, d_out_ptr, stream or None))
 

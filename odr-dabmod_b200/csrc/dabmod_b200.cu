@@ -3,10 +3,12 @@
 #include "../../include/dabmod_b200.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cerrno>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -237,6 +239,12 @@ struct dabmod_b200 {
 
     uint64_t clipped_last = 0;
     uint32_t launches_last = 0;
+
+    // file sink (dabmod_b200_process_batch_to_fd): ring of pinned host buffers, one slice each
+    static constexpr int SINK_SLOTS = 3;
+    unsigned char *sink_buf[SINK_SLOTS] = {nullptr, nullptr, nullptr};
+    size_t sink_cap = 0;
+    std::vector<cudaEvent_t> ev_out;
 
     // CFR read-outs ("clip_stats", "papr"): per-symbol records of the last launch, aggregated on the host
     DevBuf<CfrSymStat> d_cfr_stats;
@@ -997,6 +1005,8 @@ void dabmod_b200_destroy(dabmod_b200 *h)
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (auto e : h->ev_in) cudaEventDestroy(e);
     for (auto e : h->ev_done) cudaEventDestroy(e);
+    for (auto e : h->ev_out) cudaEventDestroy(e);
+    for (auto &b : h->sink_buf) if (b) cudaFreeHost(b);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -1090,6 +1100,110 @@ int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, 
         consume_cfr(h);
         h->tf_counter += n_tf;
         if (out_bytes) *out_bytes = n_tf * out_tf;
+    });
+}
+
+namespace {
+// write(2) until everything is out (OutputFile.cpp:56-67 uses fwrite and throws on a short count)
+void write_all(int fd, const unsigned char *p, size_t n)
+{
+    while (n) {
+        const ssize_t w = ::write(fd, p, n);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            throw ApiError(DABMOD_B200_EIO, std::string("OutputFile: write failed: ") + std::strerror(errno));
+        }
+        p += w;
+        n -= (size_t)w;
+    }
+}
+} // namespace
+
+int dabmod_b200_process_batch_to_fd(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, int fd, size_t *out_bytes)
+{
+    if (out_bytes) *out_bytes = 0;
+    return guard([&] {
+        if (!h || (n_tf && !bits)) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        if (fd < 0) throw ApiError(DABMOD_B200_EINVAL, "bad file descriptor");
+        if (n_tf > (size_t)h->cfg.max_batch)
+            throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
+        const size_t in_tf = h->m.tf_in_bytes, out_tf = h->out_bytes_per_tf();
+        std::lock_guard<std::mutex> lock(h->mtx);
+        CUDA_CHECK(cudaSetDevice(h->device));
+        if (h->tables_dirty) build_tables(h);
+        h->launches_last = 0;
+        h->timed.clear();
+        h->events_used = 0;
+        if (n_tf == 0) return;
+        consume_cfr(h);
+        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
+            CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
+
+        // H2D(i+2) | kernels(i+1) | D2H(i) into ring slot i % SLOTS | write(i-1) on this thread
+        const size_t slice = std::max<size_t>(1, std::min<size_t>(n_tf, (32u << 20) / out_tf));
+        const size_t n_slices = (n_tf + slice - 1) / slice;
+        if (h->sink_cap < slice * out_tf) {
+            for (auto &b : h->sink_buf) {
+                if (b) CUDA_CHECK(cudaFreeHost(b));
+                b = nullptr;
+                CUDA_CHECK(cudaHostAlloc((void **)&b, slice * out_tf, cudaHostAllocDefault));
+            }
+            h->sink_cap = slice * out_tf;
+        }
+        auto grow = [](std::vector<cudaEvent_t> &v, size_t n) {
+            while (v.size() < n) {
+                cudaEvent_t e;
+                CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                v.push_back(e);
+            }
+        };
+        grow(h->ev_in, n_slices);
+        grow(h->ev_done, n_slices);
+        grow(h->ev_out, n_slices);
+        size_t written = 0, next_write = 0;
+        auto drain = [&](size_t upto) {                      // write the slices [next_write, upto)
+            for (; next_write < upto; next_write++) {
+                const size_t t0 = next_write * slice, nt = std::min(slice, n_tf - t0);
+                CUDA_CHECK(cudaEventSynchronize(h->ev_out[next_write]));
+                write_all(fd, h->sink_buf[next_write % dabmod_b200::SINK_SLOTS], nt * out_tf);
+                written += nt * out_tf;
+            }
+        };
+        try {
+            for (size_t i = 0; i < n_slices; i++) {
+                const size_t t0 = i * slice, nt = std::min(slice, n_tf - t0);
+                if (i >= (size_t)dabmod_b200::SINK_SLOTS) drain(i - dabmod_b200::SINK_SLOTS + 1);   // the slot must be free
+                CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p + t0 * in_tf, bits + t0 * in_tf, nt * in_tf,
+                                           cudaMemcpyHostToDevice, h->s_in));
+                CUDA_CHECK(cudaEventRecord(h->ev_in[i], h->s_in));
+                CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_in[i], 0));
+                enqueue(h, h->d_bits.p + t0 * in_tf, nt, h->d_out.p + t0 * out_tf, t0, h->tf_counter + t0,
+                        h->s_compute, h->launches_last);
+                CUDA_CHECK(cudaEventRecord(h->ev_done[i], h->s_compute));
+                CUDA_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[i], 0));
+                CUDA_CHECK(cudaMemcpyAsync(h->sink_buf[i % dabmod_b200::SINK_SLOTS], h->d_out.p + t0 * out_tf, nt * out_tf,
+                                           cudaMemcpyDeviceToHost, h->s_out));
+                CUDA_CHECK(cudaEventRecord(h->ev_out[i], h->s_out));
+                if (i >= 1) drain(i);                        // whatever has landed while this slice was enqueued
+            }
+            drain(n_slices);
+        }
+        catch (...) {
+            cudaStreamSynchronize(h->s_in);
+            cudaStreamSynchronize(h->s_compute);
+            cudaStreamSynchronize(h->s_out);
+            h->tf_counter += n_tf;                           // the stream position moved, like after a throw in the reference
+            if (out_bytes) *out_bytes = written;
+            throw;
+        }
+        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF) {
+            unsigned long long v = 0;
+            CUDA_CHECK(cudaMemcpy(&v, h->d_clipped.p, sizeof(v), cudaMemcpyDeviceToHost));
+            h->clipped_last = v;
+        }
+        consume_cfr(h);
+        h->tf_counter += n_tf;
+        if (out_bytes) *out_bytes = written;
     });
 }
 

@@ -103,3 +103,51 @@ def test_config5_stream_in_pieces(dm, rate):
     ora = oracle.OracleChain(**kw)
     for i in range(2):
         assert rel_rms(whole[i], ora.process(bits[i])) < TOL, i
+
+
+def test_file_sink(dm, tmp_path):
+    """Row N2: dabmod_b200_process_batch_to_fd == OutputFile behind the chain (OutputFile.cpp:56-67): the bytes in the
+    file are the bytes process_batch returns, for a regular file and for a pipe (short writes), in several calls."""
+    import os
+    import threading
+    n = 300                                                  # 14 slices of the sink's pipeline at s16
+    rng = np.random.default_rng(2027)
+    m = oracle.mode_params(1)
+    bits = rng.integers(0, 256, (n, m.tf_bytes), dtype=np.uint8)
+    kw = dict(mode=1, fir_taps=oracle.fir_default_taps(), fmt="s16", digital_gain=0.5, max_batch=n)
+    want = dm.Modulator(**kw).process_batch(bits).tobytes()
+    mod = dm.Modulator(**kw)
+    path = str(tmp_path / "out.iq")
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        assert mod.process_batch_to_fd(bits[:100], fd) == 100 * mod.tf_out_bytes
+        assert mod.process_batch_to_fd(bits[100:], fd) == 200 * mod.tf_out_bytes
+    finally:
+        os.close(fd)
+    with open(path, "rb") as f:
+        assert f.read() == want
+    # a pipe: 64 KiB kernel buffer, so every slice goes out in many short writes
+    mod.reset()
+    r, w = os.pipe()
+    got = bytearray()
+
+    def reader():
+        while True:
+            b = os.read(r, 1 << 20)
+            if not b:
+                break
+            got.extend(b)
+
+    t = threading.Thread(target=reader)
+    t.start()
+    try:
+        assert mod.process_batch_to_fd(bits, w) == len(want)
+    finally:
+        os.close(w)
+        t.join()
+        os.close(r)
+    assert bytes(got) == want
+    # a closed descriptor: the reference's OutputFile throws, here DABMOD_B200_EIO
+    with pytest.raises(dm.DabModError) as e:
+        mod.process_batch_to_fd(bits[:2], w)
+    assert e.value.code == -6
