@@ -341,6 +341,23 @@ def measure_coder(dm, torch, stream, n_tf=1024, steps=5, warmup=3, with_cpu=True
     return res
 
 
+def measure_single_tf_latency(dm, torch, host_bits, calls=200):
+    """The real-time use of the drop-in: one transmission frame (96 ms of signal) per call through
+    dabmod_b200_process, pinned host buffers in and out -- what the ModCodec adapter does once per TF."""
+    mod = dm.Modulator(mode=MODE, fir_taps="default", max_batch=1)
+    out = torch.empty(mod.tf_out_bytes, dtype=torch.uint8).pin_memory()
+    lat = []
+    for i in range(calls + 20):
+        t0 = time.perf_counter()
+        mod.process_batch_ptr(host_bits[i % host_bits.shape[0]].data_ptr(), 1, out.data_ptr(), mod.tf_out_bytes)
+        lat.append(time.perf_counter() - t0)
+    lat = np.array(lat[20:]) * 1e6
+    mod.close()
+    return {"workload": "latency: one TF per call (dabmod_b200_process, host buffers), TM I + FIR default taps",
+            "us_median": float(np.median(lat)), "us_p99": float(np.percentile(lat, 99)), "calls": calls,
+            "realtime_budget_us": 96000}
+
+
 def measure_e2e_s16(dm, torch, host_bits, n_tf, steps=5):
     """The headline workload end to end with FormatConverter s16 fused into k_fir: `e2e` is bound by the
     PCIe link (1.57 MB of complexf per TF), so halving the output bytes is what moves it."""
@@ -531,6 +548,10 @@ def gpu_arm(args):
                 others.append(measure_config(dm, torch, name, kw, ntf, stream, peak))
             except Exception as e:                       # an extra must never cost the headline line
                 others.append({"workload": name, "error": str(e)})
+        try:
+            others.append(measure_single_tf_latency(dm, torch, host_bits))
+        except Exception as e:
+            others.append({"workload": "latency", "error": str(e)})
         try:
             others.append(measure_e2e_s16(dm, torch, host_bits, n_tf))
         except Exception as e:
