@@ -217,3 +217,26 @@ def test_eti_to_iq_on_device():
     assert got.shape[0] == 4
     for i in range(4):
         assert rel_rms(got[i], want[i]) < 2e-6, i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tm1_six_128k_3a", "tm2_mixed_eep_a", "tm3_eep_b"])
+def test_eti_to_fixed_point_iq_on_device(name):
+    """The whole reference graph for FFTEngine::KISS -- ETI bytes -> channel coding -> fixed-point OFDM -- on the
+    device: every bit of the int16 I/Q equals oracle coder + fixed-point oracle (both pinned against the reference)."""
+    dm = dabmod_loader.load()
+    mux = multiplexes()
+    if name not in mux:
+        name = sorted(mux)[0]
+    mode, subch = mux[name]
+    per_tf = {1: 4, 2: 1, 3: 1, 4: 2}[mode]
+    frames = eti_mod().synth_eti(mode, subch, 4 * per_tf, seed=5)
+    _, streams = dm.eti_describe(frames[0])
+    blocks = oracle.OracleCoder(mode, streams).run(frames)
+    want = oracle.OracleChain(mode=mode, fixed_point=True, window_overlap=8).run(np.stack(blocks))
+    mod = dm.Modulator(mode=mode, fixed_point=True, window_overlap=8, max_batch=4)
+    cod = dm.Coder(mode, streams, max_frames=4 * per_tf)
+    got = cod.modulate(mod, frames)
+    assert got.dtype == np.int16 and got.shape[0] == 4
+    for i in range(4):
+        assert np.array_equal(got[i], want[i]), i
