@@ -513,8 +513,9 @@ def gpu_arm(args):
 
     peak, peak_src = measured_peaks()
     bytes_per_launch = {"k_symbols": SYM_BYTES_PER_TF * n_tf, "k_symbols_w": SYM_BYTES_PER_TF * n_tf,
-                        "k_fir": FIR_BYTES_PER_TF * n_tf, "k_fir_sym": FIR_SYM_BYTES_PER_TF * n_tf}
-    if "k_fir_sym" in kavg:
+                        "k_fir": FIR_BYTES_PER_TF * n_tf, "k_fir_sym": FIR_SYM_BYTES_PER_TF * n_tf,
+                        "k_fir_tma": FIR_SYM_BYTES_PER_TF * n_tf}
+    if "k_fir_sym" in kavg or "k_fir_tma" in kavg:
         # compact intermediate: the symbol kernel writes 76 x 2048 samples per TF (no null symbol, no cyclic prefix)
         bytes_per_launch["k_symbols_w"] = (TF_IN_BYTES + COMPACT_SAMPLES * 8) * n_tf
     dom = max(kavg, key=lambda k: kavg[k])

@@ -203,6 +203,7 @@ struct dabmod_b200 {
     DevBuf<float> d_twiddle_w;     // second-pass table of k_symbols_w (TM I only)
     bool use_warp_kernel = true;   // "sym_kernel" knob: 0 = always the CTA-per-symbol-group kernel
     bool use_fir_sym = true;       // "fir_kernel" knob: 0 = always the sample-stream FIR kernel
+    int fir_kernel = 2;            //   1 = k_fir_sym, 2 = k_fir_tma where it applies (complexf output)
     int n_twiddle = 0;
     DevBuf<uint16_t> d_tii_bin;
     DevBuf<float> d_tii_val;
@@ -609,8 +610,16 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         for (size_t j = 0; j < h->fir_taps.size(); j++) fp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
         fp.post = make_post(h, post);
         const dim3 fgrid((unsigned)m.L, (unsigned)n_tf);
-        ProfScope prof_fir(h, "k_fir_sym", s);
-        if (post) k_fir_sym<45, true><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
+        const bool tma = !post && h->fir_kernel >= 2;
+        ProfScope prof_fir(h, tma ? "k_fir_tma" : "k_fir_sym", s);
+        if (tma) {
+            const long long n_items = (long long)n_tf * m.L;
+            const int grid = (int)std::min<long long>(n_items, (long long)h->sm_count * FIRT_CTAS_PER_SM);
+            CUDA_CHECK(cudaFuncSetAttribute(k_fir_tma<45>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)sizeof(FirTmaSmem)));
+            k_fir_tma<45><<<grid, FIRT_THREADS, sizeof(FirTmaSmem), s>>>(fp, n_items);
+        }
+        else if (post) k_fir_sym<45, true><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
         else k_fir_sym<45, false><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
         CUDA_CHECK(cudaGetLastError());
         prof_fir.end();
@@ -1311,7 +1320,7 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             else if (n == "profile") { int v; ss >> v; h->profile = v != 0; }
             else if (n == "sym_chunks") { int v; ss >> v; h->force_chunks = v < 0 ? 0 : v; }
             else if (n == "sym_kernel") { int v; ss >> v; h->use_warp_kernel = v != 0; }
-            else if (n == "fir_kernel") { int v; ss >> v; h->use_fir_sym = v != 0; }
+            else if (n == "fir_kernel") { int v; ss >> v; h->use_fir_sym = v != 0; h->fir_kernel = v; }
             else if (n == "res_kernel") { int v; ss >> v; h->allow_res_up = v != 0; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {

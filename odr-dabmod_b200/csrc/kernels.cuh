@@ -1009,6 +1009,174 @@ __global__ void __launch_bounds__(FIRS_THREADS, 8) k_fir_sym(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------
+// k_fir_tma: k_fir_sym's work (TM I, compact input, complexf output) as a persistent, TMA-fed pipeline.
+//
+// Both FIR kernels above stop at ~0.63 ms with neither HBM, the FMA pipe nor issue saturated: inside a CTA the
+// chain load -> filter -> transpose -> store is serial and the padded shared layout keeps every byte on the LSU.
+// Here a lane owns 17 consecutive outputs instead of 16: the lane stride is odd, so the window needs NO padding,
+// is conflict free as it lies in memory, and can therefore be moved by the bulk-copy engine in both directions:
+//   * input: cp.async.bulk global -> shared of the symbol's 2048 samples, the 44-sample head of the next symbol's
+//     prefix and the two seam strips, completing on an mbarrier; two stages, fetched two symbols ahead;
+//   * output: every thread parks its 17 results in natural order (stride 17 again), then three bulk copies
+//     shared -> global land body, prefix (= the outputs over the tail, straight from the same staging) and seam.
+// No global load or store instruction is left in the steady state; a CTA walks a contiguous range of symbols.
+// Threads 0..120 take the 2048 body outputs, 121..123 the 44 outputs of the prefix/body seam, 124..126 (symbol 1)
+// the 44 at the end of the null symbol -- one code path, different base pointers.  Same operands in the same
+// order as k_fir: bit-identical.
+// ---------------------------------------------------------------------------
+constexpr int FIRT_THREADS = 128;
+constexpr int FIRT_M = 17;
+constexpr int FIRT_IN = 2048 + 44 + 12;           // body | next prefix head | slack for the last body thread's window
+constexpr int FIRT_STRIP = 96;                    // 2 * 44 seam inputs + slack
+constexpr int FIRT_OUT = 2048 + 16;               // body outputs + slack for the last body thread
+constexpr int FIRT_SEAM = 64;
+constexpr int FIRT_CTAS_PER_SM = 3;
+
+struct FirTmaStage {
+    float2 in[FIRT_IN];
+    float2 strip[2][FIRT_STRIP];                  // [0]: body end ++ body start; [1]: zeros ++ prefix start (symbol 1)
+    float2 out[FIRT_OUT];
+    float2 seam[2][FIRT_SEAM];
+};
+struct FirTmaSmem {
+    FirTmaStage st[2];
+    unsigned long long full[2];                   // mbarriers: stage's input has landed
+};
+
+__device__ __forceinline__ uint32_t firt_saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void firt_load(void *sdst, const void *gsrc, int bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(firt_saddr(sdst)), "l"(__cvta_generic_to_global(gsrc)), "r"(bytes), "r"(firt_saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void firt_store(void *gdst, const void *ssrc, int bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(__cvta_generic_to_global(gdst)), "r"(firt_saddr(ssrc)), "r"(bytes) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(FIRT_THREADS, FIRT_CTAS_PER_SM) k_fir_tma(const __grid_constant__ FirSymParams p, long long n_items)
+{
+    constexpr int N = 2048, H = NT - 1;
+    static_assert(H == 44, "buffer geometry is laid out for the 45 default taps");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    FirTmaSmem &sm = *reinterpret_cast<FirTmaSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int pre = p.sym_size - N;
+    const long long per = (n_items + gridDim.x - 1) / gridDim.x;
+    const long long it0 = (long long)blockIdx.x * per;
+    const long long it1 = it0 + per < n_items ? it0 + per : n_items;
+    if (it0 >= it1) return;
+
+    // item = tf * L + (s - 1): everything the symbol's filter reads, by bulk copies onto one mbarrier
+    auto fetch = [&](long long item, int stage) {
+        const int s = 1 + (int)(item % p.L);
+        const float2 *body = p.in + (size_t)item * N;
+        FirTmaStage &st = sm.st[stage];
+        unsigned bytes = N * 8 + 2 * H * 8;
+        if (s < p.L) bytes += H * 8;
+        if (s == 1) bytes += H * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(firt_saddr(&sm.full[stage])), "r"(bytes) : "memory");
+        firt_load(st.in, body, N * 8, &sm.full[stage]);
+        if (s < p.L) firt_load(st.in + N, body + N + (N - pre), H * 8, &sm.full[stage]);      // next symbol's prefix head
+        firt_load(st.strip[0], body + N - H, H * 8, &sm.full[stage]);                          // prefix end = body end
+        firt_load(st.strip[0] + H, body, H * 8, &sm.full[stage]);                              // ... then the body start
+        if (s == 1) firt_load(st.strip[1] + H, body + (N - pre), H * 8, &sm.full[stage]);      // null symbol: zeros, then the prefix
+    };
+
+    for (int i = tid; i < 2 * FIRT_STRIP; i += FIRT_THREADS) {
+        sm.st[0].strip[i / FIRT_STRIP][i % FIRT_STRIP] = make_float2(0.f, 0.f);
+        sm.st[1].strip[i / FIRT_STRIP][i % FIRT_STRIP] = make_float2(0.f, 0.f);
+    }
+    for (int i = tid; i < FIRT_IN - N; i += FIRT_THREADS) {
+        sm.st[0].in[N + i] = make_float2(0.f, 0.f);
+        sm.st[1].in[N + i] = make_float2(0.f, 0.f);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(firt_saddr(&sm.full[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(firt_saddr(&sm.full[1])) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // zeros and barrier inits, before any bulk copy
+    __syncthreads();
+    if (tid == 0) {
+        fetch(it0, 0);
+        if (it0 + 1 < it1) fetch(it0 + 1, 1);
+    }
+
+    // this thread's share: 17 consecutive outputs of the body, or of a seam
+    const int cls = tid < 121 ? 0 : tid < 124 ? 1 : tid < 127 ? 2 : 3;
+    const int k0 = cls == 0 ? FIRT_M * tid : cls == 1 ? FIRT_M * (tid - 121) : FIRT_M * (tid - 124);
+
+    for (long long item = it0; item < it1; item++) {
+        const int it = (int)(item - it0), stage = it & 1;
+        const unsigned parity = (unsigned)(it >> 1) & 1u;
+        FirTmaStage &st = sm.st[stage];
+        const int tf = (int)(item / p.L);
+        const int s = 1 + (int)(item - (long long)tf * p.L);
+        // A. the stage's input has landed
+        {
+            unsigned done = 0;
+            const uint32_t bar = firt_saddr(&sm.full[stage]);
+            while (!done)
+                asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+        if (s == p.L) {                                      // TF end: the window runs into zeros (FIRFilter.cpp:186-191)
+            if (tid < H) st.in[N + tid] = make_float2(0.f, 0.f);
+            __syncthreads();
+        }
+        // B. filter
+        float2 acc[FIRT_M];
+#pragma unroll
+        for (int m = 0; m < FIRT_M; m++) acc[m] = make_float2(0.f, 0.f);
+        if (cls == 0 || cls == 1 || (cls == 2 && s == 1)) {
+            const float2 *x = (cls == 0 ? st.in : st.strip[cls - 1]) + k0;
+#pragma unroll
+            for (int i = 0; i < FIRT_M + NT - 1; i++) {
+                const float2 v = x[i];
+#pragma unroll
+                for (int m = 0; m < FIRT_M; m++) {
+                    const int j = i - m;
+                    if (j >= 0 && j < NT) acc[m] = __ffma2_rn(v, p.taps[j], acc[m]);
+                }
+            }
+        }
+        // C. park the results in natural order (lane stride 17: conflict free)
+        {
+            float2 *y = cls == 0 ? st.out + k0 : st.seam[cls == 2 ? 1 : 0] + k0;
+            if (cls != 3) {
+#pragma unroll
+                for (int m = 0; m < FIRT_M; m++) y[m] = acc[m];
+            }
+        }
+        // null symbol of this TF: zeros up to the seam (plain stores, one symbol in 76)
+        const size_t tf_base = (size_t)tf * p.tf_samples;
+        if (s == 1) {
+            float4 *z = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + tf_base);
+            for (int q = tid; q < (p.null_size - H) / 2; q += FIRT_THREADS) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // D. the previous symbol's bulk stores have read their staging (so the NEXT symbol may overwrite it), this
+        //    symbol's staging is complete and visible to the copy engine, nobody reads the input stage any more
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        // E. results out, input for the symbol after next in
+        if (tid == 0) {
+            float2 *g = reinterpret_cast<float2 *>(p.out) + tf_base + p.null_size + (size_t)(s - 1) * p.sym_size;
+            firt_store(g + pre, st.out, N * 8);                                   // body
+            firt_store(g, st.out + (N - pre), (pre - H) * 8);                     // prefix = outputs over the tail
+            firt_store(g + (pre - H), st.seam[0], H * 8);                         // prefix/body seam
+            if (s == 1)
+                firt_store(reinterpret_cast<float2 *>(p.out) + tf_base + (p.null_size - H), st.seam[1], H * 8);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (item + 2 < it1) fetch(item + 2, stage);
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------
 // k_post: stand-alone [MemlessPoly] -> [FormatConverter] for chains where no
 // other kernel can carry the epilogue.  Reference: see PostParams.
 // ---------------------------------------------------------------------------

@@ -81,7 +81,16 @@ def test_fir_symbol_kernel(dm, rng, kw):
     a = dm.Modulator(mode=1, fir_taps=taps, max_batch=3, **kw)
     a.set_param("profile", 1)
     ya = a.process_batch(bits)
-    assert "k_fir_sym" in [k for k, _ in a.kernel_times()]
+    # complexf straight out of the FIR: the persistent TMA-fed variant; with an epilogue (format, predistortion): k_fir_sym
+    raw = "fmt" not in kw and "poly" not in kw or "output_rate" in kw
+    assert ("k_fir_tma" if raw else "k_fir_sym") in [k for k, _ in a.kernel_times()]
+    if raw:
+        c = dm.Modulator(mode=1, fir_taps=taps, max_batch=3, **kw)
+        c.set_param("fir_kernel", 1)
+        c.set_param("profile", 1)
+        yc = c.process_batch(bits)
+        assert "k_fir_sym" in [k for k, _ in c.kernel_times()]
+        assert np.array_equal(ya.view(np.uint8), yc.view(np.uint8))
     b = dm.Modulator(mode=1, fir_taps=taps, max_batch=3, **kw)
     b.set_param("fir_kernel", 0)
     b.set_param("profile", 1)
