@@ -307,8 +307,10 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
         if (live) {
             const int n_out = P * RQ_KEEP;
             const size_t obase = (size_t)hop * n_out;
+            // e / P by multiplication: exact for e < 16384 and P = 2..5 (ceil(2^16 / P) over-estimates by < 1 / (P e))
+            const unsigned inv = (65536u + P - 1) / P;
             for (int e = t; e < n_out; e += RQ_TEAM) {
-                const int m = e / P, rho = e - m * P;
+                const int m = (int)(((unsigned)e * inv) >> 16), rho = e - m * P;
                 const float2 y = (rho == P - 1 ? buf : sm.stage[team][rho])[rq_result_slot(m)];
                 store_sample<POST>(p.out, obase + e, y, p.post, clip);
             }
