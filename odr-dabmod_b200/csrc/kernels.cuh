@@ -111,6 +111,39 @@ __device__ __forceinline__ void store_sample(void *out, size_t idx, float2 v, co
     }
 }
 
+// Four consecutive samples starting at `idx` (idx a multiple of 4): same arithmetic as store_sample, one or two
+// 16-byte stores (one 8-byte store for the one-byte formats) instead of four narrow ones.
+template <bool POST>
+__device__ __forceinline__ void store_run4(void *out, size_t idx, float2 a, float2 b, float2 c, float2 d,
+                                           const PostParams &pp, unsigned &clip)
+{
+    if (POST) { a = dpd_apply(pp, a); b = dpd_apply(pp, b); c = dpd_apply(pp, c); d = dpd_apply(pp, d); }
+    if (!POST || pp.format == 0) {
+        float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(out) + idx);
+        o[0] = make_float4(a.x, a.y, b.x, b.y);
+        o[1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+    else if (pp.format == 1) {
+        const float2 v[4] = {a, b, c, d};
+        unsigned w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            w[i] = (unsigned)(fmt_s16(v[i].x, clip) & 0xffff) | ((unsigned)(fmt_s16(v[i].y, clip) & 0xffff) << 16);
+        *reinterpret_cast<uint4 *>(reinterpret_cast<short2 *>(out) + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    else {
+        const float2 v[4] = {a, b, c, d};
+        unsigned w[2] = {0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = pp.format == 2 ? fmt_u8(v[i].x, clip) : fmt_s8(v[i].x, clip);
+            const int y = pp.format == 2 ? fmt_u8(v[i].y, clip) : fmt_s8(v[i].y, clip);
+            w[i >> 1] |= ((unsigned)(x & 0xff) | ((unsigned)(y & 0xff) << 8)) << (16 * (i & 1));
+        }
+        *reinterpret_cast<uint2 *>(reinterpret_cast<uchar2 *>(out) + idx) = make_uint2(w[0], w[1]);
+    }
+}
+
 __device__ __forceinline__ void flush_clip(const PostParams &pp, unsigned clip)
 {
     // one atomic per warp that saw clipping

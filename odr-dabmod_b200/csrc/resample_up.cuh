@@ -213,12 +213,10 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 const int m = t + 256 * r;
-                if (!POST && L == 4) {
-                    const float2 a = sm.stage[team][0][m], b = sm.stage[team][1][m];
-                    const float2 c = sm.stage[team][2][m], d = sm.stage[team][3][m];
-                    float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + obase + (size_t)m * 4);
-                    o[0] = make_float4(a.x, a.y, b.x, b.y);
-                    o[1] = make_float4(c.x, c.y, d.x, d.y);
+                if (L == 4) {
+                    // the four phases of input sample m are four consecutive output samples: 32 bytes per lane
+                    store_run4<POST>(p.out, obase + (size_t)m * 4, sm.stage[team][0][m], sm.stage[team][1][m],
+                                     sm.stage[team][2][m], sm.stage[team][3][m], p.post, clip);
                 }
                 else {
                     for (int rho = 0; rho < L; rho++)
