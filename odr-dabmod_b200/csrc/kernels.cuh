@@ -111,6 +111,27 @@ __device__ __forceinline__ void store_sample(void *out, size_t idx, float2 v, co
     }
 }
 
+// Two consecutive samples starting at an even `idx`: one store of twice the width.
+template <bool POST>
+__device__ __forceinline__ void store_run2(void *out, size_t idx, float2 a, float2 b, const PostParams &pp, unsigned &clip)
+{
+    if (POST) { a = dpd_apply(pp, a); b = dpd_apply(pp, b); }
+    if (!POST || pp.format == 0) {
+        *reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(out) + idx) = make_float4(a.x, a.y, b.x, b.y);
+    }
+    else if (pp.format == 1) {
+        const unsigned w0 = (unsigned)(fmt_s16(a.x, clip) & 0xffff) | ((unsigned)(fmt_s16(a.y, clip) & 0xffff) << 16);
+        const unsigned w1 = (unsigned)(fmt_s16(b.x, clip) & 0xffff) | ((unsigned)(fmt_s16(b.y, clip) & 0xffff) << 16);
+        *reinterpret_cast<uint2 *>(reinterpret_cast<short2 *>(out) + idx) = make_uint2(w0, w1);
+    }
+    else {
+        const int ax = pp.format == 2 ? fmt_u8(a.x, clip) : fmt_s8(a.x, clip), ay = pp.format == 2 ? fmt_u8(a.y, clip) : fmt_s8(a.y, clip);
+        const int bx = pp.format == 2 ? fmt_u8(b.x, clip) : fmt_s8(b.x, clip), by = pp.format == 2 ? fmt_u8(b.y, clip) : fmt_s8(b.y, clip);
+        *reinterpret_cast<unsigned *>(reinterpret_cast<uchar2 *>(out) + idx) =
+            (unsigned)(ax & 0xff) | ((unsigned)(ay & 0xff) << 8) | ((unsigned)(bx & 0xff) << 16) | ((unsigned)(by & 0xff) << 24);
+    }
+}
+
 // Four consecutive samples starting at `idx` (idx a multiple of 4): same arithmetic as store_sample, one or two
 // 16-byte stores (one 8-byte store for the one-byte formats) instead of four narrow ones.
 template <bool POST>

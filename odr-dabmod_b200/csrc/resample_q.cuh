@@ -309,11 +309,12 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
             const size_t obase = (size_t)hop * n_out;
             // e / P by multiplication: exact for e < 16384 and P = 2..5 (ceil(2^16 / P) over-estimates by < 1 / (P e))
             const unsigned inv = (65536u + P - 1) / P;
-            for (int e = t; e < n_out; e += RQ_TEAM) {
+            auto result = [&](int e) {                       // output sample e of the hop = phase e % P of m = e / P
                 const int m = (int)(((unsigned)e * inv) >> 16), rho = e - m * P;
-                const float2 y = (rho == P - 1 ? buf : sm.stage[team][rho])[rq_result_slot(m)];
-                store_sample<POST>(p.out, obase + e, y, p.post, clip);
-            }
+                return (rho == P - 1 ? buf : sm.stage[team][rho])[rq_result_slot(m)];
+            };
+            for (int e = 2 * t; e < n_out; e += 2 * RQ_TEAM)  // n_out and the hop's first output index are even
+                store_run2<POST>(p.out, obase + e, result(e), result(e + 1), p.post, clip);
         }
         // (the next round's first write to buf / stage comes after several team barriers)
     }
