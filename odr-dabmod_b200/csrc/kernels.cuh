@@ -57,6 +57,36 @@ __device__ __forceinline__ float2 dpd_apply(const PostParams &pp, float2 x)
     return x;
 }
 
+// The odd-polynomial predistorter on two samples at once: the Horner chains run on packed FP32 (FFMA2: same rounding
+// as two fmaf, half the issue slots).  Other modes fall back to dpd_apply.
+__device__ __forceinline__ void dpd_apply2(const PostParams &pp, float2 &a, float2 &b)
+{
+    if (pp.dpd_mode != 1) {
+        a = dpd_apply(pp, a);
+        b = dpd_apply(pp, b);
+        return;
+    }
+    const float2 mag = make_float2(fmaf(a.x, a.x, a.y * a.y), fmaf(b.x, b.x, b.y * b.y));
+    float2 amp = make_float2(pp.am[4], pp.am[4]), ph = make_float2(pp.pm[4], pp.pm[4]);
+#pragma unroll
+    for (int i = 3; i >= 0; i--) {
+        amp = __ffma2_rn(mag, amp, make_float2(pp.am[i], pp.am[i]));
+        ph = __ffma2_rn(mag, ph, make_float2(pp.pm[i], pp.pm[i]));
+    }
+    ph = make_float2(-ph.x, -ph.y);
+    const float2 p2 = __fmul2_rn(ph, ph);
+    const float2 np2 = make_float2(-p2.x, -p2.y);
+    float2 re = __ffma2_rn(p2, make_float2(-0.00138888f, -0.00138888f), make_float2(0.486666f, 0.486666f));
+    re = __ffma2_rn(p2, re, make_float2(-0.5f, -0.5f));
+    re = __ffma2_rn(np2, re, make_float2(1.0f, 1.0f));
+    float2 im = __ffma2_rn(p2, make_float2(0.00833333f, 0.00833333f), make_float2(0.166666f, 0.166666f));
+    im = __ffma2_rn(p2, im, make_float2(1.0f, 1.0f));
+    im = __fmul2_rn(ph, im);
+    const float ar = a.x * amp.x, ai = a.y * amp.x, br = b.x * amp.y, bi = b.y * amp.y;
+    a = make_float2(fmaf(ar, re.x, -ai * im.x), fmaf(ar, im.x, ai * re.x));
+    b = make_float2(fmaf(br, re.y, -bi * im.y), fmaf(br, im.y, bi * re.y));
+}
+
 // saturating conversion with C truncation, counts clipped components
 __device__ __forceinline__ int fmt_s16(float v, unsigned &clip)
 {
@@ -115,7 +145,7 @@ __device__ __forceinline__ void store_sample(void *out, size_t idx, float2 v, co
 template <bool POST>
 __device__ __forceinline__ void store_run2(void *out, size_t idx, float2 a, float2 b, const PostParams &pp, unsigned &clip)
 {
-    if (POST) { a = dpd_apply(pp, a); b = dpd_apply(pp, b); }
+    if (POST) dpd_apply2(pp, a, b);
     if (!POST || pp.format == 0) {
         *reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(out) + idx) = make_float4(a.x, a.y, b.x, b.y);
     }
@@ -138,7 +168,7 @@ template <bool POST>
 __device__ __forceinline__ void store_run4(void *out, size_t idx, float2 a, float2 b, float2 c, float2 d,
                                            const PostParams &pp, unsigned &clip)
 {
-    if (POST) { a = dpd_apply(pp, a); b = dpd_apply(pp, b); c = dpd_apply(pp, c); d = dpd_apply(pp, d); }
+    if (POST) { dpd_apply2(pp, a, b); dpd_apply2(pp, c, d); }
     if (!POST || pp.format == 0) {
         float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(out) + idx);
         o[0] = make_float4(a.x, a.y, b.x, b.y);
