@@ -88,24 +88,22 @@ __device__ __forceinline__ void dpd_apply2(const PostParams &pp, float2 &a, floa
 }
 
 // saturating conversion with C truncation, counts clipped components
+// (branch free: float -> int conversion saturates, the range test only feeds the counter)
 __device__ __forceinline__ int fmt_s16(float v, unsigned &clip)
 {
-    if (v < -32768.0f) { clip++; return -32768; }
-    if (v > 32767.0f) { clip++; return 32767; }
-    return (int)v;
+    clip += (v < -32768.0f) | (v > 32767.0f);
+    return max(-32768, min(32767, __float2int_rz(v)));
 }
 __device__ __forceinline__ int fmt_u8(float v, unsigned &clip)
 {
     const float s = v + 128.0f;
-    if (s < 0.0f) { clip++; return 0; }
-    if (s > 255.0f) { clip++; return 255; }
-    return (int)s;
+    clip += (s < 0.0f) | (s > 255.0f);
+    return max(0, min(255, __float2int_rz(s)));
 }
 __device__ __forceinline__ int fmt_s8(float v, unsigned &clip)
 {
-    if (v < -128.0f) { clip++; return -128; }
-    if (v > 127.0f) { clip++; return 127; }
-    return (int)v;
+    clip += (v < -128.0f) | (v > 127.0f);
+    return max(-128, min(127, __float2int_rz(v)));
 }
 
 // Stores complex sample number `idx` of the output stream.
