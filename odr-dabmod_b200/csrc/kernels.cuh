@@ -442,17 +442,52 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
     unsigned clip = 0;
     float gain_sym1 = 1.0f;
     int tail_par = 0;
-    for (int it = 0; it < n_iter; it++) {
-        int grp, what = EMIT;
+    // group handled by iteration `it` of the schedule above
+    auto group_of = [&](int it) {
         if (W > 0) {
-            if (grp0 > 0) { grp = grp0 - 1 + it; what = it == 0 ? TAIL_ONLY : EMIT; }
-            else if (G == 1) { grp = it == 0 ? 1 : it - 1; what = it == 0 ? GAIN_ONLY : EMIT; }
-            else grp = it;
+            if (grp0 > 0) return grp0 - 1 + it;
+            if (G == 1) return it == 0 ? 1 : it - 1;
+            return it;
         }
-        else {
-            grp = grp0 + it;
-            if (G == 1 && grp0 == 0) grp = it == 0 ? 1 : it == 1 ? 0 : it;   // neither consumes data bits
+        if (G == 1 && grp0 == 0) return it == 0 ? 1 : it == 1 ? 0 : it;   // neither consumes data bits
+        return grp0 + it;
+    };
+    // The bit rows of a group's symbols (I bits | Q bits << 16 of this thread's 16 carriers) are fetched one
+    // iteration ahead, and the carriers' FFT bins once per CTA: the carrier threads were spending 40 % of the
+    // kernel's stall samples behind these dependent loads (profiles, per-instruction samples).
+    auto fetch_rows = [&](int grp, uint32_t (&rw)[G]) {
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int s = grp * G + g;
+            rw[g] = 0;
+            if (s >= 2 && s <= p.L) {
+                const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
+                rw[g] = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row)) |
+                        ((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row + K / 8)) << 16);
+            }
         }
+    };
+    uint32_t rows[G], binp[8];
+#pragma unroll
+    for (int g = 0; g < G; g++) rows[g] = 0;
+#pragma unroll
+    for (int n = 0; n < 8; n++) binp[n] = 0;
+    if (carrier_thread) {
+        fetch_rows(group_of(0), rows);
+#pragma unroll
+        for (int n = 0; n < 8; n++) binp[n] = __ldg(reinterpret_cast<const uint32_t *>(p.bin_of_src + 16 * jj) + n);
+    }
+    for (int it = 0; it < n_iter; it++) {
+        const int grp = group_of(it);
+        int what = EMIT;
+        if (W > 0) {
+            if (grp0 > 0) what = it == 0 ? TAIL_ONLY : EMIT;
+            else if (G == 1) what = it == 0 ? GAIN_ONLY : EMIT;
+        }
+        uint32_t cur[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) cur[g] = rows[g];
+        if (carrier_thread && it + 1 < n_iter) fetch_rows(group_of(it + 1), rows);
         if (!OPT && G == 1 && grp == 0 && !tii_on) {
             // plain null symbol: all-zero carriers -> all-zero samples
             const size_t pos = out_base;
@@ -480,9 +515,7 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
             for (int g = 0; g < G; g++) {
                 const int s = s0 + g;
                 if (s >= 2 && s <= p.L) {
-                    const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
-                    const unsigned iw = __ldg(reinterpret_cast<const unsigned short *>(row));
-                    const unsigned qw = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
+                    const unsigned iw = cur[g] & 0xffffu, qw = cur[g] >> 16;
                     ph_lo = (ph_lo + phase_step(sm.spread, iw & 0xff, qw & 0xff)) & 0x77777777u;
                     ph_hi = (ph_hi + phase_step(sm.spread, iw >> 8, qw >> 8)) & 0x77777777u;
                 }
@@ -502,7 +535,7 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
                     const float f = __ldg(p.cic + j);
                     v.x *= f; v.y *= f;
                 }
-                dst[spad(fbase + __ldg(p.bin_of_src + j))] = v;
+                dst[spad(fbase + (int)((n & 1) ? binp[n >> 1] >> 16 : binp[n >> 1] & 0xffffu))] = v;
             }
         }
         __syncthreads();
