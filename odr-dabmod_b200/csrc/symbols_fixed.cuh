@@ -295,20 +295,47 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
         }
     }
 
+    // bit rows one group ahead, digit-reversed carrier positions once per CTA (as in k_symbols)
+    auto fetch_rows = [&](int grp, uint32_t (&rw)[G]) {
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int s = grp * G + g;
+            rw[g] = 0;
+            if (s >= 2 && s <= p.L) {
+                const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
+                rw[g] = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row)) |
+                        ((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row + K / 8)) << 16);
+            }
+        }
+    };
+    uint32_t rows[G], posp[8];
+#pragma unroll
+    for (int g = 0; g < G; g++) rows[g] = 0;
+#pragma unroll
+    for (int n = 0; n < 8; n++) posp[n] = 0;
+    if (carrier_thread) {
+        fetch_rows(grp0, rows);
+#pragma unroll
+        for (int n = 0; n < 8; n++) posp[n] = __ldg(reinterpret_cast<const uint32_t *>(p.pos_of_src + 16 * jj) + n);
+    }
+
     for (int grp = grp0; grp < grp1; grp++) {
         const int s0 = grp * G;
+        uint32_t cur[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) cur[g] = rows[g];
+        if (carrier_thread && grp + 1 < grp1) fetch_rows(grp + 1, rows);
         // ---- 1. carriers into their digit-reversed positions; everything else is zero ----
         for (int i = tid; i < FX_BUF; i += FX_THREADS) sm.buf[i] = 0u;
         __syncthreads();
         if (carrier_thread) {
             uint32_t my_lo = 0, my_hi = 0;
             bool mine = false;
+#pragma unroll
             for (int g = 0; g < G; g++) {
                 const int s = s0 + g;
                 if (s >= 2 && s <= p.L) {
-                    const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
-                    const unsigned iw = __ldg(reinterpret_cast<const unsigned short *>(row));
-                    const unsigned qw = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
+                    const unsigned iw = cur[g] & 0xffffu, qw = cur[g] >> 16;
                     ph_lo = (ph_lo + 0x11111111u + 2u * sm.spread[(iw ^ qw) & 0xff] + 4u * sm.spread[qw & 0xff]) & 0x77777777u;
                     ph_hi = (ph_hi + 0x11111111u + 2u * sm.spread[((iw ^ qw) >> 8) & 0xff] + 4u * sm.spread[qw >> 8]) & 0x77777777u;
                 }
@@ -319,7 +346,8 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
                 for (int n = 0; n < 16; n++) {
                     const unsigned ph = ((n < 8 ? my_lo >> (4 * n) : my_hi >> (4 * (n - 8)))) & 7u;
                     const short2 c = sm.c8[ph];
-                    sm.buf[fxpad(cg * N + __ldg(p.pos_of_src + 16 * jj + n))] = (uint32_t)(uint16_t)c.x | ((uint32_t)(uint16_t)c.y << 16);
+                    const int pos = (int)((n & 1) ? posp[n >> 1] >> 16 : posp[n >> 1] & 0xffffu);
+                    sm.buf[fxpad(cg * N + pos)] = (uint32_t)(uint16_t)c.x | ((uint32_t)(uint16_t)c.y << 16);
                 }
             }
         }
