@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
     const int chunk = blockIdx.x - tf * p.n_chunks;
     const int grp0 = chunk * p.groups_per_chunk;
     const int grp1 = min(grp0 + p.groups_per_chunk, p.n_groups);
-    const int K = p.K;
+    constexpr int K = N * 3 / 4;              // carriers of the mode (p.K), a compile-time fact here: divisions by constants
     const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
     const size_t out_base = (size_t)tf * p.tf_samples;
     const bool tii_on = p.tii_count > 0 && (((p.tf_offset + tf + p.tii_parity) & 1) == 0);
