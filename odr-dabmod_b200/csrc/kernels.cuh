@@ -455,25 +455,26 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
     // The bit rows of a group's symbols (I bits | Q bits << 16 of this thread's 16 carriers) are fetched one
     // iteration ahead, and the carriers' FFT bins once per CTA: the carrier threads were spending 40 % of the
     // kernel's stall samples behind these dependent loads (profiles, per-instruction samples).
-    auto fetch_rows = [&](int grp, uint32_t (&rw)[G]) {
+    auto fetch_rows = [&](int grp, unsigned short (&ri)[G], unsigned short (&rq)[G]) {
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const int s = grp * G + g;
-            rw[g] = 0;
-            if (s >= 2 && s <= p.L) {
+            ri[g] = 0; rq[g] = 0;
+            if (s >= 2 && s <= p.L) {               // (the values are not touched before the next iteration)
                 const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
-                rw[g] = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row)) |
-                        ((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row + K / 8)) << 16);
+                ri[g] = __ldg(reinterpret_cast<const unsigned short *>(row));
+                rq[g] = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
             }
         }
     };
-    uint32_t rows[G], binp[8];
+    unsigned short rows_i[G], rows_q[G];
+    uint32_t binp[8];
 #pragma unroll
-    for (int g = 0; g < G; g++) rows[g] = 0;
+    for (int g = 0; g < G; g++) { rows_i[g] = 0; rows_q[g] = 0; }
 #pragma unroll
     for (int n = 0; n < 8; n++) binp[n] = 0;
     if (carrier_thread) {
-        fetch_rows(group_of(0), rows);
+        fetch_rows(group_of(0), rows_i, rows_q);
 #pragma unroll
         for (int n = 0; n < 8; n++) binp[n] = __ldg(reinterpret_cast<const uint32_t *>(p.bin_of_src + 16 * jj) + n);
     }
@@ -484,10 +485,10 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
             if (grp0 > 0) what = it == 0 ? TAIL_ONLY : EMIT;
             else if (G == 1) what = it == 0 ? GAIN_ONLY : EMIT;
         }
-        uint32_t cur[G];
+        unsigned cur_i[G], cur_q[G];
 #pragma unroll
-        for (int g = 0; g < G; g++) cur[g] = rows[g];
-        if (carrier_thread && it + 1 < n_iter) fetch_rows(group_of(it + 1), rows);
+        for (int g = 0; g < G; g++) { cur_i[g] = rows_i[g]; cur_q[g] = rows_q[g]; }
+        if (carrier_thread && it + 1 < n_iter) fetch_rows(group_of(it + 1), rows_i, rows_q);
         if (!OPT && G == 1 && grp == 0 && !tii_on) {
             // plain null symbol: all-zero carriers -> all-zero samples
             const size_t pos = out_base;
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
             for (int g = 0; g < G; g++) {
                 const int s = s0 + g;
                 if (s >= 2 && s <= p.L) {
-                    const unsigned iw = cur[g] & 0xffffu, qw = cur[g] >> 16;
+                    const unsigned iw = cur_i[g], qw = cur_q[g];
                     ph_lo = (ph_lo + phase_step(sm.spread, iw & 0xff, qw & 0xff)) & 0x77777777u;
                     ph_hi = (ph_hi + phase_step(sm.spread, iw >> 8, qw >> 8)) & 0x77777777u;
                 }

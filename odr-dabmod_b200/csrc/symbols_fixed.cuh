@@ -296,35 +296,36 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
     }
 
     // bit rows one group ahead, digit-reversed carrier positions once per CTA (as in k_symbols)
-    auto fetch_rows = [&](int grp, uint32_t (&rw)[G]) {
+    auto fetch_rows = [&](int grp, unsigned short (&ri)[G], unsigned short (&rq)[G]) {
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const int s = grp * G + g;
-            rw[g] = 0;
-            if (s >= 2 && s <= p.L) {
+            ri[g] = 0; rq[g] = 0;
+            if (s >= 2 && s <= p.L) {               // (the values are not touched before the next iteration)
                 const uint8_t *row = bits + (size_t)(s - 2) * (K / 4) + 2 * jj;
-                rw[g] = (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row)) |
-                        ((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(row + K / 8)) << 16);
+                ri[g] = __ldg(reinterpret_cast<const unsigned short *>(row));
+                rq[g] = __ldg(reinterpret_cast<const unsigned short *>(row + K / 8));
             }
         }
     };
-    uint32_t rows[G], posp[8];
+    unsigned short rows_i[G], rows_q[G];
+    uint32_t posp[8];
 #pragma unroll
-    for (int g = 0; g < G; g++) rows[g] = 0;
+    for (int g = 0; g < G; g++) { rows_i[g] = 0; rows_q[g] = 0; }
 #pragma unroll
     for (int n = 0; n < 8; n++) posp[n] = 0;
     if (carrier_thread) {
-        fetch_rows(grp0, rows);
+        fetch_rows(grp0, rows_i, rows_q);
 #pragma unroll
         for (int n = 0; n < 8; n++) posp[n] = __ldg(reinterpret_cast<const uint32_t *>(p.pos_of_src + 16 * jj) + n);
     }
 
     for (int grp = grp0; grp < grp1; grp++) {
         const int s0 = grp * G;
-        uint32_t cur[G];
+        unsigned cur_i[G], cur_q[G];
 #pragma unroll
-        for (int g = 0; g < G; g++) cur[g] = rows[g];
-        if (carrier_thread && grp + 1 < grp1) fetch_rows(grp + 1, rows);
+        for (int g = 0; g < G; g++) { cur_i[g] = rows_i[g]; cur_q[g] = rows_q[g]; }
+        if (carrier_thread && grp + 1 < grp1) fetch_rows(grp + 1, rows_i, rows_q);
         // ---- 1. carriers into their digit-reversed positions; everything else is zero ----
         for (int i = tid; i < FX_BUF; i += FX_THREADS) sm.buf[i] = 0u;
         __syncthreads();
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
             for (int g = 0; g < G; g++) {
                 const int s = s0 + g;
                 if (s >= 2 && s <= p.L) {
-                    const unsigned iw = cur[g] & 0xffffu, qw = cur[g] >> 16;
+                    const unsigned iw = cur_i[g], qw = cur_q[g];
                     ph_lo = (ph_lo + 0x11111111u + 2u * sm.spread[(iw ^ qw) & 0xff] + 4u * sm.spread[qw & 0xff]) & 0x77777777u;
                     ph_hi = (ph_hi + 0x11111111u + 2u * sm.spread[((iw ^ qw) >> 8) & 0xff] + 4u * sm.spread[qw >> 8]) & 0x77777777u;
                 }
