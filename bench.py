@@ -378,6 +378,206 @@ def measure_e2e_s16(dm, torch, host_bits, n_tf, steps=5):
             "d2h_GB/s": out_bytes * steps / dt / 1e9, "steps": steps}
 
 
+# ---------------------------------------------------------------------------
+# BASELINE configs[4]: ONE ETI stream sharded across the ranks by transmission-frame range
+# ---------------------------------------------------------------------------
+STREAM_WORKLOAD = "TM I full chain, 65536-frame synthetic ETI stream sharded across 8xB200, resample to 10 Msps"
+STREAM_KW = dict(mode=1, fir_taps="default", output_rate=10000000, normalise=1.0 / 46000.0, poly=POLY)
+SEAM_TFS = 2
+
+
+def measure_sharded_stream(dm, torch, dist, rank, world, local_rank, n_eti_frames, batch_tfs=256):
+    """One stream of n_eti_frames ETI(NI) frames -> channel coding -> TM I symbols -> FIR -> 10 Msps -> MemlessPoly,
+    cut into contiguous transmission-frame ranges, one per rank (sharding.plan_shards).  Rank r positions coder and
+    modulator with dabmod_b200_seek_eti (15 ETI frames of time-interleaver history + the TF before the shard re-run
+    for the resampler overlap + TII parity) and streams its range in calls of `batch_tfs` TFs.  No data-path
+    collective.  Parity gate: rank r runs SEAM_TFS frames past its range with its continuous state; their CRC must
+    equal the CRC of the first SEAM_TFS frames of rank r+1, which started from seek_eti."""
+    import importlib
+    import zlib
+    eti = importlib.import_module("odr_dabmod_b200.eti")
+    sharding = importlib.import_module("odr_dabmod_b200.sharding")
+    cif = 4
+    n_tf = n_eti_frames // cif
+    plan = sharding.plan_shards(n_tf, world)
+    sh = plan[rank]
+    mux = eti.default_multiplex()
+    f0 = sh.first_tf * cif
+    hist = min(f0, 15 + cif)
+    tail = SEAM_TFS * cif if sh.first_tf + sh.n_tf + SEAM_TFS <= n_tf else 0
+    n_local = hist + sh.n_tf * cif + tail
+    host_eti = torch.empty((max(n_local, 1), 6144), dtype=torch.uint8).pin_memory()
+    eti.synth_eti_range(1, mux, f0 - hist, n_local, seed=1234, out=host_eti.numpy())
+    frames = host_eti.numpy()
+    mode, streams = dm.eti_describe(frames[0])
+    B = min(batch_tfs, max(sh.n_tf, SEAM_TFS))
+    stream = torch.cuda.Stream()
+    res = {"workload": STREAM_WORKLOAD, "eti_frames": n_eti_frames, "tfs": n_tf, "ranks": world,
+           "tfs_per_rank": [s.n_tf for s in plan], "tfs_per_call": B, "output": "complexf, 960000 samples per TF",
+           "collective": "none on the data path (control-plane all_gather of CRCs and timings only)"}
+
+    def sync_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_formats(fmt):
+        kw = dict(STREAM_KW)
+        if fmt != "complexf":
+            kw["fmt"] = fmt
+        mod = dm.Modulator(max_batch=B, device=local_rank, **kw)
+        cod = dm.Coder(mode, streams, max_frames=B * cif, device=local_rank)
+        return mod, cod
+
+    mod, cod = run_formats("complexf")
+    out_tf = mod.tf_out_bytes
+    d_eti = host_eti.to("cuda")
+    d_bits = torch.empty(B * cod.tf_bytes, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(B * out_tf, dtype=torch.uint8, device="cuda")
+    shard_eti = hist * 6144                      # byte offset of the shard's first frame in the local buffers
+
+    def device_pass(collect):
+        """seek + the shard's calls, enqueued on `stream`; returns (seek seconds, [crc of the first SEAM_TFS], crc of the tail)"""
+        t0 = time.perf_counter()
+        cod.seek(mod, sh.first_tf, frames[:hist])
+        seek_s = time.perf_counter() - t0
+        head = tailcrc = None
+        for t in range(0, sh.n_tf, B):
+            n = min(B, sh.n_tf - t)
+            cod.process_device(d_eti.data_ptr() + shard_eti + t * cif * 6144, n * cif, d_bits.data_ptr(), stream.cuda_stream)
+            mod.process_batch_device(d_bits.data_ptr(), n, d_out.data_ptr(), stream.cuda_stream)
+            if collect and t == 0:
+                stream.synchronize()
+                head = zlib.crc32(d_out[:min(SEAM_TFS, n) * out_tf].cpu().numpy().tobytes())
+        if collect and tail:
+            t = sh.n_tf
+            cod.process_device(d_eti.data_ptr() + shard_eti + t * cif * 6144, tail, d_bits.data_ptr(), stream.cuda_stream)
+            mod.process_batch_device(d_bits.data_ptr(), SEAM_TFS, d_out.data_ptr(), stream.cuda_stream)
+            stream.synchronize()
+            tailcrc = zlib.crc32(d_out[:SEAM_TFS * out_tf].cpu().numpy().tobytes())
+        return seek_s, head, tailcrc
+
+    # ---- pass 1 (untimed, also the warm-up): seam CRCs ----
+    head = tailcrc = None
+    if sh.n_tf:
+        _, head, tailcrc = device_pass(True)
+    torch.cuda.synchronize()
+    crcs = [(head, tailcrc)]
+    if dist is not None:
+        crcs = [None] * world
+        dist.all_gather_object(crcs, (head, tailcrc))
+    seams = [(r, crcs[r][1], crcs[r + 1][0]) for r in range(world - 1)
+             if crcs[r][1] is not None and crcs[r + 1][0] is not None and plan[r + 1].n_tf >= SEAM_TFS]
+    res["seam_parity"] = {"seams_checked": len(seams), "tfs_per_seam": SEAM_TFS,
+                          "bit_identical": all(a == b for _, a, b in seams),
+                          "how": "CRC32 of the I/Q of the %d TFs after each seam: continued by rank r (stream state) "
+                                 "vs started by rank r+1 (seek_eti)" % SEAM_TFS,
+                          "crc": [{"seam_after_rank": r, "continued": a, "seeked": b} for r, a, b in seams]}
+    if world == 1 and n_tf >= 4 * SEAM_TFS:
+        # one rank: the same gate against a second handle that seeks to the middle of the stream
+        mid = n_tf // 2
+        mod2, cod2 = run_formats("complexf")
+        cod2.seek(mod2, mid, frames[hist + mid * cif - (15 + cif): hist + mid * cif])
+        a = cod2.modulate(mod2, frames[hist + mid * cif: hist + (mid + SEAM_TFS) * cif])
+        cod.seek(mod, mid - SEAM_TFS, frames[hist + (mid - SEAM_TFS) * cif - min((mid - SEAM_TFS) * cif, 15 + cif):
+                                             hist + (mid - SEAM_TFS) * cif])
+        b = cod.modulate(mod, frames[hist + (mid - SEAM_TFS) * cif: hist + (mid + SEAM_TFS) * cif])[SEAM_TFS:]
+        res["seam_parity"].update({"seams_checked": 1, "bit_identical": bool(np.array_equal(a.view(np.uint32), b.view(np.uint32))),
+                                   "how": "one rank: %d TFs at mid-stream, a handle that ran into them vs a second handle "
+                                          "started there with seek_eti, compared bit for bit" % SEAM_TFS})
+        mod2.close()
+        cod2.close()
+    if not res["seam_parity"]["bit_identical"]:
+        raise SystemExit("bench.py: sharded stream: seam parity FAILED: %r" % (res["seam_parity"],))
+
+    # ---- pass 2: device-resident (ETI frames and I/Q in HBM; the I/Q of a call is overwritten by the next) ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    seek_s = 0.0
+    if sh.n_tf:
+        seek_s, _, _ = device_pass(False)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = sync_max(time.perf_counter() - t_wall)
+    dev_ms = sync_max(e0.elapsed_time(e1))         # includes the (synchronous) seek of this rank
+    seek_ms = sync_max(seek_s * 1e3)
+    res["device_resident"] = {"eti_frames_per_s": n_eti_frames / (dev_ms * 1e-3), "ms": dev_ms, "seek_ms": seek_ms,
+                              "wall_ms": wall * 1e3,
+                              "timing": "CUDA events on the launching stream around seek_eti + every call of the shard, "
+                                        "max over ranks"}
+    launches = mod.last_launch_count
+    res["kernels_per_call"] = launches + 2
+    mod.close()
+    cod.close()
+    del d_out, d_bits
+
+    # ---- pass 3: host-delivered (ETI frames from pinned host memory, I/Q into pinned host memory) ----
+    for fmt in ("complexf", "s16"):
+        mod, cod = run_formats(fmt)
+        out_tf = mod.tf_out_bytes
+        host_out = torch.empty(B * out_tf, dtype=torch.uint8).pin_memory()
+        base = host_eti.data_ptr() + shard_eti
+        check = 0
+        if sh.n_tf:                                  # warm-up call (buffers touched, pipeline events created)
+            cod.seek(mod, sh.first_tf, frames[:hist])
+            cod.modulate_ptr(mod, base, min(B, sh.n_tf) * cif, host_out.data_ptr(), host_out.numel())
+        barrier()
+        t0 = time.perf_counter()
+        if sh.n_tf:
+            cod.seek(mod, sh.first_tf, frames[:hist])
+            for t in range(0, sh.n_tf, B):
+                n = min(B, sh.n_tf - t)
+                cod.modulate_ptr(mod, base + t * cif * 6144, n * cif, host_out.data_ptr(), host_out.numel())
+                check ^= int(host_out[::1048573].to(torch.int64).sum().item())    # the delivered bytes are read
+        dt = sync_max(time.perf_counter() - t0)
+        res["host_delivered_" + fmt] = {"eti_frames_per_s": n_eti_frames / dt, "s": dt,
+                                        "d2h_bytes": n_tf * out_tf, "d2h_GB/s": n_tf * out_tf / dt / 1e9,
+                                        "h2d_bytes": n_eti_frames * 6144, "checksum": check,
+                                        "timing": "wall clock around seek_eti + dabmod_b200_process_eti_batch calls "
+                                                  "(pinned host buffers both ways), max over ranks"}
+        if fmt == "complexf" and dist is not None:
+            # ---- result gather over NCCL ("NCCL only for result gather"), a bounded sample, timed separately ----
+            g_tfs = min(64, min(s.n_tf for s in plan))
+            if g_tfs > 0:
+                dev = torch.device("cuda", local_rank)
+                mine = host_out[:g_tfs * out_tf].to(dev).view(g_tfs, out_tf)
+                my_crc = zlib.crc32(mine.cpu().numpy().tobytes())
+                sub = [sharding.Shard(r, r * g_tfs, g_tfs) for r in range(world)]
+                sharding.gather_stream(mine, sub, dist, dst=0, device=dev)        # warm-up (NCCL communicator setup)
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                full = sharding.gather_stream(mine, sub, dist, dst=0, device=dev)
+                g1.record()
+                torch.cuda.synchronize()
+                g_ms = sync_max(g0.elapsed_time(g1))
+                all_crc = [None] * world
+                dist.all_gather_object(all_crc, my_crc)
+                ordered = None
+                if rank == 0:
+                    ordered = all(zlib.crc32(full[r * g_tfs:(r + 1) * g_tfs].cpu().numpy().tobytes()) == all_crc[r]
+                                  for r in range(world))
+                res["nccl_gather"] = {"tfs_per_rank": g_tfs, "bytes_to_rank0": world * g_tfs * out_tf, "ms": g_ms,
+                                      "GB/s": world * g_tfs * out_tf / (g_ms * 1e-3) / 1e9, "in_stream_order": ordered,
+                                      "note": "sharding.gather_stream (torch.distributed gather over NCCL/NVLink) of a "
+                                              "bounded sample; the full 126 GB stream is drained per rank, not gathered"}
+                del mine, full
+        mod.close()
+        cod.close()
+        del host_out
+    torch.cuda.empty_cache()
+    return res
+
+
+
 def bind_to_gpu_numa_node(gpu_index):
     """Run this rank (and allocate its pinned host buffers) on the CPUs next to its GPU: the end-to-end leg
     moves 1.6 GB per step over PCIe, and a remote NUMA node costs a third of that bandwidth."""
@@ -502,6 +702,19 @@ def gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     checksum = int(host_out[::65537].to(torch.int64).sum().item())  # the D2H result is read (strided over the whole buffer)
 
+    # ---- BASELINE configs[4]: one ETI stream sharded across the ranks (every rank takes part) ----
+    sharded = None
+    if args.stream_frames > 0:
+        mod.close()
+        d_bits = d_out = host_out = None             # 3.2 GB of HBM and 1.6 GB of pinned memory back before the stream leg
+        torch.cuda.empty_cache()
+        try:
+            sharded = measure_sharded_stream(dm, torch, dist, rank, world, local_rank, args.stream_frames)
+        except SystemExit:
+            raise
+        except Exception as e:                      # never lose the headline line
+            sharded = {"workload": STREAM_WORKLOAD, "error": "%s: %s" % (type(e).__name__, e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -580,6 +793,9 @@ def gpu_arm(args):
         "roofline": roofline,
         "clocks": clocks,
     }
+    if sharded is not None:
+        line["sharded_stream"] = sharded
+        line["config"]["sharded_stream_workload"] = STREAM_WORKLOAD
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if others is not None:
@@ -599,6 +815,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--only", default="", help="development: measure only the other_configs entry with this prefix")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (other_configs key)")
+    ap.add_argument("--stream-frames", type=int, default=65536,
+                    help="ETI frames of the sharded-stream leg (BASELINE configs[4]); 0 skips it")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

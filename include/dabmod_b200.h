@@ -131,11 +131,17 @@ int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf,
 int dabmod_b200_process_batch_to_fd(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, int fd, size_t *out_bytes);
 
 /* Same, device-resident buffers on the handle's device; enqueued on `stream`
- * (a cudaStream_t, NULL = the handle's own stream) and NOT synchronised. */
+ * (a cudaStream_t, NULL = the handle's own stream) and NOT synchronised.
+ * Successive calls on one handle are ordered by the library whatever their streams (an event recorded after
+ * each enqueue is waited for by the next): the work buffers, the resampler history and the tables belong to
+ * the handle.  With CFR enabled the call first waits on the host for the previous one (its per-symbol records
+ * are read back before they are overwritten).  The FormatConverter clip count of such a call is read back by
+ * dabmod_b200_num_clipped_samples / dabmod_b200_synchronize, which wait for it. */
 int dabmod_b200_process_batch_device(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf,
                                      void *d_iq_out, void *stream);
 
-/* Blocks until everything enqueued on the handle's own streams is done. */
+/* Blocks until everything enqueued for the handle (its own streams and the stream of the last
+ * dabmod_b200_process_batch_device call) is done. */
 int dabmod_b200_synchronize(dabmod_b200 *h);
 
 /* Forget the stream history: Resampler overlap buffers (src/Resampler.cpp:110-111)
@@ -259,9 +265,25 @@ int dabmod_b200_coder_reset(dabmod_b200_coder *c);
 int dabmod_b200_coder_prime(dabmod_b200_coder *c, const uint8_t *eti_frames, size_t n_frames);
 
 /* ETI bytes in, I/Q out: coder and modulator chained on the device (the coded blocks never
- * travel to the host).  Both handles must be on the same device and transmission mode. */
+ * travel to the host).  Both handles must be on the same device and transmission mode.  Same sliced
+ * three-stream pipeline as dabmod_b200_process_batch: ETI frames of slice i+1 cross PCIe while slice i is in
+ * the coding + modulator kernels and the I/Q of slice i-1 goes back.  This is the whole of
+ * DabModulator::process (src/DabModulator.cpp:131-417) for n_frames / frames_per_tf transmission frames. */
 int dabmod_b200_process_eti_batch(dabmod_b200 *h, dabmod_b200_coder *c, const uint8_t *eti_frames, size_t n_frames,
                                   void *iq_out, size_t cap, size_t *out_bytes);
+/* Same, delivered to a file descriptor through the modulator's pinned ring (src/OutputFile.cpp:56-67). */
+int dabmod_b200_process_eti_batch_to_fd(dabmod_b200 *h, dabmod_b200_coder *c, const uint8_t *eti_frames,
+                                        size_t n_frames, int fd, size_t *out_bytes);
+
+/* Positions coder + modulator at transmission frame `tf_index` of a stream, for sharding one ETI stream across
+ * GPUs by frame ranges (BASELINE configs[4]).  `eti_before` = the `n_before` ETI frames that precede the shard
+ * in the stream; the last min(tf_index * frames_per_tf, 15 + frames_per_tf) of them are used and that many are
+ * required: 15 frames rebuild the time interleaver memory (src/TimeInterleaver.cpp:39-41,66-93), the
+ * transmission frame before the shard is coded and re-run up to the resampler input to rebuild the Resampler
+ * overlap (src/Resampler.cpp:143-145,185-191); tf_index sets the TII every-second-frame toggle
+ * (src/TII.cpp:225-242).  The shard's output is then bit-identical to the same frames of an unsharded run. */
+int dabmod_b200_seek_eti(dabmod_b200 *h, dabmod_b200_coder *c, uint64_t tf_index, const uint8_t *eti_before,
+                         size_t n_before);
 
 /* Thread-local description of the last coder error. Never NULL. */
 const char *dabmod_b200_coder_last_error(void);

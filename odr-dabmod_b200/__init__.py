@@ -39,7 +39,8 @@ EXPORTS = [
     "dabmod_b200_eti_describe", "dabmod_b200_coder_create", "dabmod_b200_coder_destroy",
     "dabmod_b200_coder_tf_bytes", "dabmod_b200_coder_frames_per_tf", "dabmod_b200_coder_process",
     "dabmod_b200_coder_process_device", "dabmod_b200_coder_reset", "dabmod_b200_coder_prime",
-    "dabmod_b200_process_eti_batch", "dabmod_b200_coder_last_error",
+    "dabmod_b200_process_eti_batch", "dabmod_b200_process_eti_batch_to_fd", "dabmod_b200_seek_eti",
+    "dabmod_b200_coder_last_error",
 ]
 
 
@@ -153,6 +154,8 @@ def lib():
     L.dabmod_b200_coder_reset.argtypes = [vp]
     L.dabmod_b200_coder_prime.argtypes = [vp, vp, sz]
     L.dabmod_b200_process_eti_batch.argtypes = [vp, vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
+    L.dabmod_b200_process_eti_batch_to_fd.argtypes = [vp, vp, vp, sz, ctypes.c_int, ctypes.POINTER(sz)]
+    L.dabmod_b200_seek_eti.argtypes = [vp, vp, ctypes.c_uint64, vp, sz]
     L.dabmod_b200_coder_last_error.restype = ctypes.c_char_p
     _lib = L
     return L
@@ -437,6 +440,28 @@ class Coder:
                                                          out.ctypes.data, out.size, ctypes.byref(nb)))
         flat = out[:nb.value].view(modulator.out_dtype)
         return flat.reshape(n_tf, flat.size // n_tf if n_tf else 0)
+
+    def modulate_ptr(self, modulator, eti_ptr, n_frames, out_ptr, out_cap):
+        """Raw host pointers (e.g. pinned torch tensors): dabmod_b200_process_eti_batch."""
+        nb = ctypes.c_size_t()
+        _check_coder(lib().dabmod_b200_process_eti_batch(modulator._h, self._h, eti_ptr, n_frames, out_ptr, out_cap,
+                                                         ctypes.byref(nb)))
+        return nb.value
+
+    def modulate_to_fd(self, modulator, frames, fd):
+        """ETI frames -> I/Q written to the descriptor `fd` (the reference's OutputFile sink); returns bytes written."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        nb = ctypes.c_size_t()
+        _check_coder(lib().dabmod_b200_process_eti_batch_to_fd(modulator._h, self._h, frames.ctypes.data,
+                                                               frames.size // ETI_FRAME, fd, ctypes.byref(nb)))
+        return nb.value
+
+    def seek(self, modulator, tf_index, frames_before):
+        """Position coder + modulator at transmission frame `tf_index` of the stream; `frames_before` = the ETI frames
+        that precede it (at least min(tf_index * frames_per_tf, 15 + frames_per_tf) of them)."""
+        fb = np.ascontiguousarray(frames_before, np.uint8)
+        _check_coder(lib().dabmod_b200_seek_eti(modulator._h, self._h, tf_index, fb.ctypes.data if fb.size else None,
+                                                fb.size // ETI_FRAME))
 
     def close(self):
         if getattr(self, "_h", None):

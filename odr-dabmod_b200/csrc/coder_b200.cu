@@ -12,6 +12,7 @@
 // frames is one flat grid of (frame, stream, output word) items.  The only memory across
 // frames is the time interleaver's (15 frames), kept as a ring of punctured frames.
 #include "../../include/dabmod_b200.h"
+#include "internal.h"
 
 #include <cuda_runtime.h>
 
@@ -30,10 +31,7 @@ constexpr int ETI_FRAME = 6144;
 constexpr int TI_DEPTH = 16;             // TimeInterleaver history, frames
 constexpr int MAX_STREAMS = 65;
 
-struct CoderError : std::runtime_error {
-    int code;
-    CoderError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
-};
+using CoderError = dabmod::ApiError;     // one error type across the library, so that codes survive the chain
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -305,6 +303,15 @@ int dabmod_b200_eti_describe(const uint8_t *frame, size_t len, int *mode, dabmod
             else throw CoderError(DABMOD_B200_EINVAL, "SubchannelSource unknown protection option!");
         }
         *n_streams = (int)nst + 1;
+        // InputFileReader.cpp:84 accepts a frame by its FSYNC word; EtiReader then consumes STC, EOH, the FIC and
+        // every stream (EtiReader.cpp:190-249) -- a frame shorter than that is a truncated read.
+        const uint32_t sync = (uint32_t)frame[1] | ((uint32_t)frame[2] << 8) | ((uint32_t)frame[3] << 16);
+        if (sync != 0xb63a07u && sync != 0x49c5f8u) throw CoderError(DABMOD_B200_EINVAL, "ETI frame without FSYNC");
+        size_t need = 8 + 4 * (size_t)nst + 4 + st[0].framesize;
+        for (unsigned i = 0; i < nst; i++) need += st[1 + i].framesize;
+        if (len < need)
+            throw CoderError(DABMOD_B200_EINVAL, "ETI frame too short for its header: " + std::to_string(len) + " < " +
+                                                     std::to_string(need));
     });
 }
 
@@ -353,27 +360,29 @@ int dabmod_b200_coder_create(int device, int mode, const dabmod_b200_stream *st,
                 throw CoderError(DABMOD_B200_EINVAL, "BlockPartitioner::process input 0 size not valid!");
             if (s > 0 && d.start_cu * 8 + d.out_bytes > (uint32_t)CIF_BYTES)
                 throw CoderError(DABMOD_B200_EINVAL, "subchannel exceeds the CIF");
-            // The puncturing rules (PuncturingEncoder.cpp:148-196) as a table of segments: rules are
-            // consumed in order and cycled, each covers length/4 groups of 4 encoder bytes.
+            // The puncturing rules (PuncturingEncoder.cpp:148-196) as a table of segments, each covering
+            // length/4 groups of 4 encoder bytes.  The reference sizes its input block from the rules
+            // (adjust_item_size, :55-78) and throws "wrong input size" (:137-140) unless they cover the
+            // ConvEncoder output exactly: every rule is applied once, over its full length.
             StreamDev sd{};
             const long groups = d.framesize;                     // 4 encoder bytes per input byte
             long g = 0, ob = 0;
-            uint32_t r = 0;
-            while (g < groups) {
+            for (uint32_t r = 0; r < d.n_rules; r++) {
                 if (d.rules[r].length == 0 || (d.rules[r].length & 3))
                     throw CoderError(DABMOD_B200_EINVAL, "puncturing rule length must be a positive multiple of 4");
-                if (sd.n_segments == MAX_SEGMENTS)
-                    throw CoderError(DABMOD_B200_EUNSUPPORTED, "more than 16 puncturing rule applications per frame");
                 Segment &sg = sd.seg[sd.n_segments++];
                 sg.first_group = (int)g;
-                sg.n_groups = (int)std::min<long>(d.rules[r].length / 4, groups - g);
+                sg.n_groups = (int)(d.rules[r].length / 4);
                 sg.mask = d.rules[r].pattern;
                 sg.kept = __builtin_popcount(sg.mask);
                 sg.out_bit = (int)ob;
                 g += sg.n_groups;
                 ob += (long)sg.n_groups * sg.kept;
-                if (++r == d.n_rules) r = 0;
             }
+            if (g != groups)
+                throw CoderError(DABMOD_B200_EINVAL, "PuncturingEncoder::process wrong input size: the rules of stream " +
+                                                         std::to_string(s) + " cover " + std::to_string(4 * g + 3) +
+                                                         " encoder bytes, the ConvEncoder emits " + std::to_string(4 * groups + 3));
             sd.tail_out_bit = (int)ob;
             ob += 12;                                            // tail rule (3, 0xcccccc), DabModulator.cpp:316,373
             // PuncturingEncoder.cpp:120-134: the kept bits must fill the block (UEP: one byte of padding allowed)
@@ -525,34 +534,106 @@ int dabmod_b200_coder_prime(dabmod_b200_coder *c, const uint8_t *eti, size_t n_f
     });
 }
 
+} // extern "C"
+
+namespace {
+// The coder as the front of the modulator's sliced pipeline: ETI frames cross PCIe on the copy stream, the
+// coding kernels run on the modulator's compute stream right before the symbol kernels of the same slice,
+// the coded blocks never leave the device.  Caller holds the coder's lock.
+dabmod::PipeFront eti_front(dabmod_b200_coder *c, const uint8_t *eti)
+{
+    dabmod::PipeFront f;
+    const size_t cif = (size_t)c->cif_count;
+    f.upload = [c, eti, cif](size_t t0, size_t nt, cudaStream_t s_in) {
+        CK(cudaMemcpyAsync(c->d_eti + t0 * cif * ETI_FRAME, eti + t0 * cif * ETI_FRAME, nt * cif * ETI_FRAME,
+                           cudaMemcpyHostToDevice, s_in));
+    };
+    f.encode = [c, cif](size_t t0, size_t nt, cudaStream_t s) -> const uint8_t * {
+        uint8_t *blocks = c->d_bits + t0 * (size_t)c->tf_bytes;
+        coder_enqueue(c, c->d_eti + t0 * cif * ETI_FRAME, nt * cif, blocks, s);
+        return blocks;
+    };
+    return f;
+}
+
+void check_chain(dabmod_b200 *h, dabmod_b200_coder *c, size_t n_frames)
+{
+    if (n_frames > (size_t)c->max_frames) throw CoderError(DABMOD_B200_EINVAL, "n_frames exceeds max_frames of the coder");
+    if (n_frames % c->cif_count) throw CoderError(DABMOD_B200_ESTATE, "a call must carry whole transmission frames");
+    if ((size_t)c->tf_bytes != dabmod_b200_tf_in_bytes(h))
+        throw CoderError(DABMOD_B200_EINVAL, "coder and modulator are configured for different transmission modes");
+    if (c->device != dabmod::device_of(h)) throw CoderError(DABMOD_B200_EINVAL, "coder and modulator are on different devices");
+}
+} // namespace
+
+extern "C" {
+
 int dabmod_b200_process_eti_batch(dabmod_b200 *h, dabmod_b200_coder *c, const uint8_t *eti, size_t n_frames,
                                   void *iq_out, size_t cap, size_t *out_bytes)
 {
     if (out_bytes) *out_bytes = 0;
-    int rc = guard([&] {
+    return guard([&] {
         if (!h || !c || (n_frames && (!eti || !iq_out))) throw CoderError(DABMOD_B200_EINVAL, "null argument");
-        if (n_frames > (size_t)c->max_frames) throw CoderError(DABMOD_B200_EINVAL, "n_frames exceeds max_frames of the coder");
-        if (n_frames % c->cif_count) throw CoderError(DABMOD_B200_ESTATE, "a call must carry whole transmission frames");
-        if ((size_t)c->tf_bytes != dabmod_b200_tf_in_bytes(h))
-            throw CoderError(DABMOD_B200_EINVAL, "coder and modulator are configured for different transmission modes");
-        const size_t n_tf = n_frames / c->cif_count;
-        const size_t nb = n_tf * dabmod_b200_tf_out_bytes(h);
-        if (cap < nb) throw CoderError(DABMOD_B200_EINVAL, "output buffer too small");
-        if (n_frames == 0) return;
-        void *d_iq = dabmod_b200_device_out(h);
-        if (!d_iq) throw CoderError(DABMOD_B200_ESTATE, "modulator has no device output buffer");
+        check_chain(h, c, n_frames);
+        std::lock_guard<std::mutex> lock(c->mtx);
+        dabmod::PipeSink sink;
+        sink.host_out = iq_out;
+        sink.cap = cap;
+        dabmod::run_pipeline(h, n_frames / c->cif_count, eti_front(c, eti), sink, out_bytes);
+    });
+}
+
+int dabmod_b200_process_eti_batch_to_fd(dabmod_b200 *h, dabmod_b200_coder *c, const uint8_t *eti, size_t n_frames,
+                                        int fd, size_t *out_bytes)
+{
+    if (out_bytes) *out_bytes = 0;
+    return guard([&] {
+        if (!h || !c || (n_frames && !eti)) throw CoderError(DABMOD_B200_EINVAL, "null argument");
+        check_chain(h, c, n_frames);
+        std::lock_guard<std::mutex> lock(c->mtx);
+        dabmod::PipeSink sink;
+        sink.to_fd = true;
+        sink.fd = fd;
+        dabmod::run_pipeline(h, n_frames / c->cif_count, eti_front(c, eti), sink, out_bytes);
+    });
+}
+
+int dabmod_b200_seek_eti(dabmod_b200 *h, dabmod_b200_coder *c, uint64_t tf_index, const uint8_t *eti_before,
+                         size_t n_before)
+{
+    return guard([&] {
+        if (!h || !c || (n_before && !eti_before)) throw CoderError(DABMOD_B200_EINVAL, "null argument");
+        check_chain(h, c, 0);
+        const size_t cif = (size_t)c->cif_count;
+        const size_t want = (size_t)std::min<uint64_t>(tf_index * cif, (uint64_t)(TI_DEPTH - 1) + cif);
+        if (n_before < want)
+            throw CoderError(DABMOD_B200_EINVAL, "seek_eti: " + std::to_string(want) + " ETI frames before the shard are "
+                                                 "needed (time interleaver depth + one transmission frame), got " +
+                                                 std::to_string(n_before));
         std::lock_guard<std::mutex> lock(c->mtx);
         CK(cudaSetDevice(c->device));
-        CK(cudaMemcpyAsync(c->d_eti, eti, n_frames * ETI_FRAME, cudaMemcpyHostToDevice, c->stream));
-        coder_enqueue(c, c->d_eti, n_frames, c->d_bits, c->stream);
-        // the coded blocks never leave the device: the modulator kernels follow on the same stream
-        if (dabmod_b200_process_batch_device(h, c->d_bits, n_tf, d_iq, c->stream) != DABMOD_B200_OK)
-            throw CoderError(DABMOD_B200_EINVAL, dabmod_b200_last_error());
-        CK(cudaMemcpyAsync(iq_out, d_iq, nb, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemsetAsync(c->d_punct, 0, (size_t)c->ring_rows * c->row_bytes, c->stream));
+        c->ring_base = 0;
+        if (tf_index == 0) {
+            CK(cudaStreamSynchronize(c->stream));
+            dabmod::seek_device(h, 0, nullptr);
+            return;
+        }
+        // the frames that matter: 15 of time-interleaver history, then the transmission frame before the shard
+        eti_before += (n_before - want) * ETI_FRAME;
+        const size_t n_hist = want - cif;
+        for (size_t done = 0; done < n_hist;) {
+            const size_t n = std::min<size_t>(n_hist - done, (size_t)c->max_frames);
+            CK(cudaMemcpyAsync(c->d_eti, eti_before + done * ETI_FRAME, n * ETI_FRAME, cudaMemcpyHostToDevice, c->stream));
+            coder_enqueue(c, c->d_eti, n, nullptr, c->stream);
+            CK(cudaStreamSynchronize(c->stream));       // d_eti is reused by the next chunk
+            done += n;
+        }
+        CK(cudaMemcpyAsync(c->d_eti, eti_before + n_hist * ETI_FRAME, cif * ETI_FRAME, cudaMemcpyHostToDevice, c->stream));
+        coder_enqueue(c, c->d_eti, cif, c->d_bits, c->stream);
         CK(cudaStreamSynchronize(c->stream));
-        if (out_bytes) *out_bytes = nb;
+        dabmod::seek_device(h, tf_index, c->d_bits);    // re-runs that frame up to the resampler input
     });
-    return rc;
 }
 
 int dabmod_b200_coder_reset(dabmod_b200_coder *c)

@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "internal.h"
 #include "kernels.cuh"
 #include "resample.cuh"
 #include "resample_up.cuh"
@@ -31,11 +32,6 @@ using namespace dabmod;
 namespace {
 
 thread_local std::string g_last_error;
-
-struct ApiError : std::runtime_error {
-    int code;
-    ApiError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
-};
 
 #define CUDA_CHECK(expr)                                                                  \
     do {                                                                                  \
@@ -239,7 +235,14 @@ struct dabmod_b200 {
     size_t res_smem = 0;
 
     uint64_t clipped_last = 0;
+    bool clipped_pending = false;  // a device-path call left its count in d_clipped (read back on demand)
     uint32_t launches_last = 0;
+
+    // Calls on one handle are stream-ordered by the library: every enqueue records `ev_last` on the stream it
+    // used and the next one (whatever its stream) waits for it, because the work buffers, the resampler history
+    // and the tables are per handle.  `ev_tables` orders a table rebuild (on s_compute) before a user stream.
+    cudaEvent_t ev_last = nullptr, ev_tables = nullptr;
+    bool have_last = false;
 
     // file sink (dabmod_b200_process_batch_to_fd): ring of pinned host buffers, one slice each
     static constexpr int SINK_SLOTS = 3;
@@ -252,7 +255,6 @@ struct dabmod_b200 {
     CfrReadouts cfr_readouts;
     bool cfr_collect = true;       // false while seek() re-runs a frame that is not part of this handle's range
     size_t cfr_pending = 0;        // TFs whose records wait in d_cfr_stats
-    cudaStream_t cfr_stream = nullptr;
 
     // optional per-kernel timing
     bool profile = false;
@@ -304,7 +306,7 @@ void build_tables(dabmod_b200 *h)
     h->use_cic = cic_enabled(c.clock_rate, rate, ratio);
     std::vector<float> cic_pos;
     if (h->use_cic) {
-        cic_pos = cic_filter(m.K, (float)m.N * (float)rate / 2048000.0f, (int)ratio);
+        cic_pos = cic_filter(m.K, (float)m.N * (float)rate / 2048000.0f, (int)ratio);   // truncates like the reference's size_t parameter
         std::vector<float> cic_src(m.K);
         for (int j = 0; j < m.K; j++) cic_src[j] = cic_pos[dest[j]];
         h->d_cic.upload(cic_src, s);
@@ -494,7 +496,7 @@ void consume_cfr(dabmod_b200 *h)
     const size_t n_sym = (size_t)h->m.L + 1;
     std::vector<CfrSymStat> rec(h->cfr_pending * n_sym);
     CUDA_CHECK(cudaSetDevice(h->device));
-    CUDA_CHECK(cudaStreamSynchronize(h->cfr_stream));
+    if (h->have_last) CUDA_CHECK(cudaEventSynchronize(h->ev_last));   // the enqueue that wrote them
     CUDA_CHECK(cudaMemcpy(rec.data(), h->d_cfr_stats.p, rec.size() * sizeof(CfrSymStat), cudaMemcpyDeviceToHost));
     for (size_t tf = 0; tf < h->cfr_pending; tf++)
         h->cfr_readouts.add_frame(rec.data() + tf * n_sym, (int)n_sym, h->m.N);
@@ -543,7 +545,6 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         if (!h->d_cfr_stats.p) h->d_cfr_stats.alloc((size_t)c.max_batch * (m.L + 1));
         sp.cfr_stats = h->d_cfr_stats.p + tmp_tf0 * (size_t)(m.L + 1);
         h->cfr_pending = std::max(h->cfr_pending, tmp_tf0 + n_tf);
-        h->cfr_stream = s;
     }
     sp.gain_mode = c.gain_mode;
     sp.gain_const = c.normalise * c.digital_gain;
@@ -930,6 +931,8 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming));
 
         h->m = mode_info(h->cfg.mode);
         std::vector<float> tw;
@@ -1011,6 +1014,9 @@ void dabmod_b200_destroy(dabmod_b200 *h)
     if (h->s_compute) cudaStreamSynchronize(h->s_compute);
     if (h->s_in) cudaStreamSynchronize(h->s_in);
     if (h->s_out) cudaStreamSynchronize(h->s_out);
+    if (h->have_last) cudaEventSynchronize(h->ev_last);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
+    if (h->ev_tables) cudaEventDestroy(h->ev_tables);
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (auto e : h->ev_in) cudaEventDestroy(e);
     for (auto e : h->ev_done) cudaEventDestroy(e);
@@ -1026,93 +1032,47 @@ size_t dabmod_b200_tf_in_bytes(const dabmod_b200 *h) { return h ? (size_t)h->m.t
 size_t dabmod_b200_tf_out_bytes(const dabmod_b200 *h) { return h ? h->out_bytes_per_tf() : 0; }
 size_t dabmod_b200_tf_out_samples(const dabmod_b200 *h) { return h ? h->out_samples_per_tf() : 0; }
 
-int dabmod_b200_process_batch_device(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_iq_out,
-                                     void *stream)
-{
-    return guard([&] {
-        if (!h || (n_tf && (!d_bits || !d_iq_out))) throw ApiError(DABMOD_B200_EINVAL, "null argument");
-        if (n_tf > (size_t)h->cfg.max_batch)
-            throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
-        if ((reinterpret_cast<uintptr_t>(d_bits) & 3) || (reinterpret_cast<uintptr_t>(d_iq_out) & 15))
-            throw ApiError(DABMOD_B200_EINVAL, "device buffers must be aligned (bits: 4 bytes, I/Q: 16 bytes)");
-        std::lock_guard<std::mutex> lock(h->mtx);
-        CUDA_CHECK(cudaSetDevice(h->device));
-        cudaStream_t s = stream ? (cudaStream_t)stream : h->s_compute;
-        if (h->tables_dirty) {
-            build_tables(h);
-            if (s != h->s_compute) CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
-        }
-        h->launches_last = 0;
-        h->timed.clear();
-        h->events_used = 0;
-        if (n_tf == 0) return;
-        consume_cfr(h);      // the records of the previous launch, before this one overwrites them
-        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
-            CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), s));
-        enqueue(h, d_bits, n_tf, d_iq_out, 0, h->tf_counter, s, h->launches_last);
-        h->tf_counter += n_tf;
-    });
-}
-
-int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, void *iq_out, size_t cap,
-                              size_t *out_bytes)
-{
-    if (out_bytes) *out_bytes = 0;
-    return guard([&] {
-        if (!h || (n_tf && (!bits || !iq_out))) throw ApiError(DABMOD_B200_EINVAL, "null argument");
-        if (n_tf > (size_t)h->cfg.max_batch)
-            throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
-        const size_t in_tf = h->m.tf_in_bytes, out_tf = h->out_bytes_per_tf();
-        if (cap < n_tf * out_tf) throw ApiError(DABMOD_B200_EINVAL, "output buffer too small");
-        std::lock_guard<std::mutex> lock(h->mtx);
-        CUDA_CHECK(cudaSetDevice(h->device));
-        if (h->tables_dirty) build_tables(h);
-        h->launches_last = 0;
-        h->timed.clear();
-        h->events_used = 0;
-        if (n_tf == 0) return;
-        consume_cfr(h);
-        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
-            CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
-
-        // Software pipeline over slices of the batch: H2D(i+1) | kernels(i) | D2H(i-1)
-        // on three streams, so PCIe traffic in both directions hides the compute.
-        const size_t slice = std::max<size_t>(1, std::min<size_t>(n_tf, (48u << 20) / out_tf));
-        const size_t n_slices = (n_tf + slice - 1) / slice;
-        while (h->ev_in.size() < n_slices) {
-            cudaEvent_t a, b;
-            CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-            CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-            h->ev_in.push_back(a);
-            h->ev_done.push_back(b);
-        }
-        for (size_t i = 0; i < n_slices; i++) {
-            const size_t t0 = i * slice, nt = std::min(slice, n_tf - t0);
-            CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p + t0 * in_tf, bits + t0 * in_tf, nt * in_tf,
-                                       cudaMemcpyHostToDevice, h->s_in));
-            CUDA_CHECK(cudaEventRecord(h->ev_in[i], h->s_in));
-            CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_in[i], 0));
-            enqueue(h, h->d_bits.p + t0 * in_tf, nt, h->d_out.p + t0 * out_tf, t0, h->tf_counter + t0,
-                    h->s_compute, h->launches_last);
-            CUDA_CHECK(cudaEventRecord(h->ev_done[i], h->s_compute));
-            CUDA_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[i], 0));
-            CUDA_CHECK(cudaMemcpyAsync((unsigned char *)iq_out + t0 * out_tf, h->d_out.p + t0 * out_tf,
-                                       nt * out_tf, cudaMemcpyDeviceToHost, h->s_out));
-        }
-        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF) {
-            CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
-            unsigned long long v = 0;
-            CUDA_CHECK(cudaMemcpy(&v, h->d_clipped.p, sizeof(v), cudaMemcpyDeviceToHost));
-            h->clipped_last = v;
-        }
-        CUDA_CHECK(cudaStreamSynchronize(h->s_out));
-        consume_cfr(h);
-        h->tf_counter += n_tf;
-        if (out_bytes) *out_bytes = n_tf * out_tf;
-    });
-}
+} // extern "C"
 
 namespace {
+
+// Start of every call that enqueues work on stream `s`: order it after the previous call on this handle
+// (work buffers, resampler history and tables are per handle) and rebuild the tables if a parameter changed.
+void begin_call(dabmod_b200 *h, cudaStream_t s)
+{
+    if (h->tables_dirty) {
+        // kernels of the previous call may still be reading the tables
+        if (h->have_last) CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_last, 0));
+        build_tables(h);
+        if (s != h->s_compute) {
+            CUDA_CHECK(cudaEventRecord(h->ev_tables, h->s_compute));
+            CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_tables, 0));
+        }
+    }
+    if (h->have_last) CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_last, 0));
+    h->launches_last = 0;
+    h->timed.clear();
+    h->events_used = 0;
+}
+
+void end_call(dabmod_b200 *h, cudaStream_t s)
+{
+    CUDA_CHECK(cudaEventRecord(h->ev_last, s));
+    h->have_last = true;
+}
+
+// FormatConverter::get_num_clipped_samples of a call whose result was left on the device
+void refresh_clipped(dabmod_b200 *h)
+{
+    if (!h->clipped_pending) return;
+    CUDA_CHECK(cudaSetDevice(h->device));
+    if (h->have_last) CUDA_CHECK(cudaEventSynchronize(h->ev_last));
+    unsigned long long v = 0;
+    CUDA_CHECK(cudaMemcpy(&v, h->d_clipped.p, sizeof(v), cudaMemcpyDeviceToHost));
+    h->clipped_last = v;
+    h->clipped_pending = false;
+}
+
 // write(2) until everything is out (OutputFile.cpp:56-67 uses fwrite and throws on a short count)
 void write_all(int fd, const unsigned char *p, size_t n)
 {
@@ -1126,7 +1086,207 @@ void write_all(int fd, const unsigned char *p, size_t n)
         n -= (size_t)w;
     }
 }
+
+void grow_events(std::vector<cudaEvent_t> &v, size_t n)
+{
+    while (v.size() < n) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        v.push_back(e);
+    }
+}
+
+void seek_locked(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits, bool on_device)
+{
+    h->tf_counter = tf_index;
+    if (!h->has_res) return;
+    CUDA_CHECK(cudaSetDevice(h->device));
+    cudaStream_t s = h->s_compute;
+    begin_call(h, s);
+    if (!prev_bits || tf_index == 0) {
+        CUDA_CHECK(cudaMemsetAsync(h->d_hist.p, 0, sizeof(float2) * h->rp.ni, s));
+    }
+    else {
+        // re-run TF tf_index-1 up to the resampler input; keep its last Ni samples
+        const uint8_t *d_prev = prev_bits;
+        if (!on_device) {
+            CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p, prev_bits, h->m.tf_in_bytes, cudaMemcpyHostToDevice, s));
+            d_prev = h->d_bits.p;
+        }
+        float2 *front = h->has_fir() ? h->d_tmp2.p : h->d_tmp.p;
+        uint32_t launches = 0;
+        consume_cfr(h);
+        h->cfr_collect = false;           // the halo frame belongs to the previous shard's read-outs
+        try {
+            enqueue_front(h, d_prev, 1, front, false, 0, tf_index - 1, s, launches);
+        }
+        catch (...) {
+            h->cfr_collect = true;
+            throw;
+        }
+        h->cfr_collect = true;
+        CUDA_CHECK(cudaMemcpyAsync(h->d_hist.p, front + h->m.tf_samples - h->rp.ni, sizeof(float2) * h->rp.ni,
+                                   cudaMemcpyDeviceToDevice, s));
+    }
+    end_call(h, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 } // namespace
+
+namespace dabmod {
+
+cudaStream_t compute_stream(dabmod_b200 *h) { return h->s_compute; }
+int device_of(const dabmod_b200 *h) { return h->device; }
+
+void seek_device(dabmod_b200 *h, uint64_t tf_index, const uint8_t *d_prev_bits)
+{
+    std::lock_guard<std::mutex> lock(h->mtx);
+    seek_locked(h, tf_index, d_prev_bits, true);
+}
+
+// Software pipeline over slices of the batch on three streams, so that PCIe traffic in both directions hides
+// behind the kernels:   H2D(i+1) | front + kernels(i) | D2H(i-1)   [| write(i-2) on this thread for a descriptor]
+void run_pipeline(dabmod_b200 *h, size_t n_tf, const PipeFront &front, const PipeSink &sink, size_t *out_bytes)
+{
+    if (out_bytes) *out_bytes = 0;
+    if (!h) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+    const bool to_fd = sink.to_fd;
+    if (to_fd && sink.fd < 0) throw ApiError(DABMOD_B200_EINVAL, "bad file descriptor");
+    if (!to_fd && n_tf && !sink.host_out) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+    if (n_tf > (size_t)h->cfg.max_batch) throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
+    const size_t out_tf = h->out_bytes_per_tf();
+    if (!to_fd && sink.cap < n_tf * out_tf) throw ApiError(DABMOD_B200_EINVAL, "output buffer too small");
+    std::lock_guard<std::mutex> lock(h->mtx);
+    CUDA_CHECK(cudaSetDevice(h->device));
+    begin_call(h, h->s_compute);
+    if (n_tf == 0) return;
+    consume_cfr(h);      // the records of the previous launch, before this one overwrites them
+    const bool count_clips = h->cfg.format != DABMOD_B200_FMT_COMPLEXF;
+    if (count_clips) CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
+    h->clipped_pending = false;
+
+    const size_t slice = std::max<size_t>(1, std::min<size_t>(n_tf, ((to_fd ? 32u : 48u) << 20) / out_tf));
+    const size_t n_slices = (n_tf + slice - 1) / slice;
+    if (to_fd && h->sink_cap < slice * out_tf) {
+        for (auto &b : h->sink_buf) {
+            if (b) CUDA_CHECK(cudaFreeHost(b));
+            b = nullptr;
+            CUDA_CHECK(cudaHostAlloc((void **)&b, slice * out_tf, cudaHostAllocDefault));
+        }
+        h->sink_cap = slice * out_tf;
+    }
+    grow_events(h->ev_in, n_slices);
+    grow_events(h->ev_done, n_slices);
+    if (to_fd) grow_events(h->ev_out, n_slices);
+
+    size_t delivered = 0, next_write = 0;
+    auto drain = [&](size_t upto) {                      // write the slices [next_write, upto) to the descriptor
+        for (; next_write < upto; next_write++) {
+            const size_t t0 = next_write * slice, nt = std::min(slice, n_tf - t0);
+            CUDA_CHECK(cudaEventSynchronize(h->ev_out[next_write]));
+            write_all(sink.fd, h->sink_buf[next_write % dabmod_b200::SINK_SLOTS], nt * out_tf);
+            delivered += nt * out_tf;
+        }
+    };
+    try {
+        for (size_t i = 0; i < n_slices; i++) {
+            const size_t t0 = i * slice, nt = std::min(slice, n_tf - t0);
+            if (to_fd && i >= (size_t)dabmod_b200::SINK_SLOTS) drain(i - dabmod_b200::SINK_SLOTS + 1);   // the slot must be free
+            front.upload(t0, nt, h->s_in);
+            CUDA_CHECK(cudaEventRecord(h->ev_in[i], h->s_in));
+            CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_in[i], 0));
+            const uint8_t *d_blocks = front.encode(t0, nt, h->s_compute);
+            enqueue(h, d_blocks, nt, h->d_out.p + t0 * out_tf, t0, h->tf_counter + t0, h->s_compute, h->launches_last);
+            CUDA_CHECK(cudaEventRecord(h->ev_done[i], h->s_compute));
+            CUDA_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[i], 0));
+            unsigned char *dst = to_fd ? h->sink_buf[i % dabmod_b200::SINK_SLOTS] : (unsigned char *)sink.host_out + t0 * out_tf;
+            CUDA_CHECK(cudaMemcpyAsync(dst, h->d_out.p + t0 * out_tf, nt * out_tf, cudaMemcpyDeviceToHost, h->s_out));
+            if (to_fd) {
+                CUDA_CHECK(cudaEventRecord(h->ev_out[i], h->s_out));
+                if (i >= 1) drain(i);                    // whatever has landed while this slice was enqueued
+            }
+        }
+        end_call(h, h->s_compute);
+        if (to_fd) drain(n_slices);
+        else {
+            CUDA_CHECK(cudaStreamSynchronize(h->s_out));
+            delivered = n_tf * out_tf;
+        }
+    }
+    catch (...) {
+        cudaStreamSynchronize(h->s_in);
+        cudaStreamSynchronize(h->s_compute);
+        cudaStreamSynchronize(h->s_out);
+        h->tf_counter += n_tf;                           // the stream position moved, like after a throw in the reference
+        if (out_bytes) *out_bytes = delivered;
+        throw;
+    }
+    if (count_clips) {
+        unsigned long long v = 0;
+        CUDA_CHECK(cudaMemcpy(&v, h->d_clipped.p, sizeof(v), cudaMemcpyDeviceToHost));
+        h->clipped_last = v;
+    }
+    consume_cfr(h);
+    h->tf_counter += n_tf;
+    if (out_bytes) *out_bytes = delivered;
+}
+
+} // namespace dabmod
+
+namespace {
+// the plain front: the input already is BlockPartitioner blocks in host memory
+PipeFront host_blocks_front(dabmod_b200 *h, const uint8_t *bits)
+{
+    const size_t in_tf = h->m.tf_in_bytes;
+    PipeFront f;
+    f.upload = [h, bits, in_tf](size_t t0, size_t nt, cudaStream_t s_in) {
+        CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p + t0 * in_tf, bits + t0 * in_tf, nt * in_tf, cudaMemcpyHostToDevice, s_in));
+    };
+    f.encode = [h, in_tf](size_t t0, size_t, cudaStream_t) -> const uint8_t * { return h->d_bits.p + t0 * in_tf; };
+    return f;
+}
+} // namespace
+
+extern "C" {
+
+int dabmod_b200_process_batch_device(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *d_iq_out,
+                                     void *stream)
+{
+    return guard([&] {
+        if (!h || (n_tf && (!d_bits || !d_iq_out))) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        if (n_tf > (size_t)h->cfg.max_batch)
+            throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
+        if ((reinterpret_cast<uintptr_t>(d_bits) & 3) || (reinterpret_cast<uintptr_t>(d_iq_out) & 15))
+            throw ApiError(DABMOD_B200_EINVAL, "device buffers must be aligned (bits: 4 bytes, I/Q: 16 bytes)");
+        std::lock_guard<std::mutex> lock(h->mtx);
+        CUDA_CHECK(cudaSetDevice(h->device));
+        cudaStream_t s = stream ? (cudaStream_t)stream : h->s_compute;
+        begin_call(h, s);
+        if (n_tf == 0) return;
+        consume_cfr(h);      // CFR on: waits for the previous call, its records are overwritten by this one
+        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF) {
+            CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), s));
+            h->clipped_pending = true;
+        }
+        enqueue(h, d_bits, n_tf, d_iq_out, 0, h->tf_counter, s, h->launches_last);
+        end_call(h, s);
+        h->tf_counter += n_tf;
+    });
+}
+
+int dabmod_b200_process_batch(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, void *iq_out, size_t cap,
+                              size_t *out_bytes)
+{
+    if (out_bytes) *out_bytes = 0;
+    return guard([&] {
+        if (!h || (n_tf && (!bits || !iq_out))) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        PipeSink sink;
+        sink.host_out = iq_out;
+        sink.cap = cap;
+        run_pipeline(h, n_tf, host_blocks_front(h, bits), sink, out_bytes);
+    });
+}
 
 int dabmod_b200_process_batch_to_fd(dabmod_b200 *h, const uint8_t *bits, size_t n_tf, int fd, size_t *out_bytes)
 {
@@ -1134,85 +1294,10 @@ int dabmod_b200_process_batch_to_fd(dabmod_b200 *h, const uint8_t *bits, size_t 
     return guard([&] {
         if (!h || (n_tf && !bits)) throw ApiError(DABMOD_B200_EINVAL, "null argument");
         if (fd < 0) throw ApiError(DABMOD_B200_EINVAL, "bad file descriptor");
-        if (n_tf > (size_t)h->cfg.max_batch)
-            throw ApiError(DABMOD_B200_EINVAL, "n_tf exceeds max_batch of the handle");
-        const size_t in_tf = h->m.tf_in_bytes, out_tf = h->out_bytes_per_tf();
-        std::lock_guard<std::mutex> lock(h->mtx);
-        CUDA_CHECK(cudaSetDevice(h->device));
-        if (h->tables_dirty) build_tables(h);
-        h->launches_last = 0;
-        h->timed.clear();
-        h->events_used = 0;
-        if (n_tf == 0) return;
-        consume_cfr(h);
-        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF)
-            CUDA_CHECK(cudaMemsetAsync(h->d_clipped.p, 0, sizeof(unsigned long long), h->s_compute));
-
-        // H2D(i+2) | kernels(i+1) | D2H(i) into ring slot i % SLOTS | write(i-1) on this thread
-        const size_t slice = std::max<size_t>(1, std::min<size_t>(n_tf, (32u << 20) / out_tf));
-        const size_t n_slices = (n_tf + slice - 1) / slice;
-        if (h->sink_cap < slice * out_tf) {
-            for (auto &b : h->sink_buf) {
-                if (b) CUDA_CHECK(cudaFreeHost(b));
-                b = nullptr;
-                CUDA_CHECK(cudaHostAlloc((void **)&b, slice * out_tf, cudaHostAllocDefault));
-            }
-            h->sink_cap = slice * out_tf;
-        }
-        auto grow = [](std::vector<cudaEvent_t> &v, size_t n) {
-            while (v.size() < n) {
-                cudaEvent_t e;
-                CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                v.push_back(e);
-            }
-        };
-        grow(h->ev_in, n_slices);
-        grow(h->ev_done, n_slices);
-        grow(h->ev_out, n_slices);
-        size_t written = 0, next_write = 0;
-        auto drain = [&](size_t upto) {                      // write the slices [next_write, upto)
-            for (; next_write < upto; next_write++) {
-                const size_t t0 = next_write * slice, nt = std::min(slice, n_tf - t0);
-                CUDA_CHECK(cudaEventSynchronize(h->ev_out[next_write]));
-                write_all(fd, h->sink_buf[next_write % dabmod_b200::SINK_SLOTS], nt * out_tf);
-                written += nt * out_tf;
-            }
-        };
-        try {
-            for (size_t i = 0; i < n_slices; i++) {
-                const size_t t0 = i * slice, nt = std::min(slice, n_tf - t0);
-                if (i >= (size_t)dabmod_b200::SINK_SLOTS) drain(i - dabmod_b200::SINK_SLOTS + 1);   // the slot must be free
-                CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p + t0 * in_tf, bits + t0 * in_tf, nt * in_tf,
-                                           cudaMemcpyHostToDevice, h->s_in));
-                CUDA_CHECK(cudaEventRecord(h->ev_in[i], h->s_in));
-                CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_in[i], 0));
-                enqueue(h, h->d_bits.p + t0 * in_tf, nt, h->d_out.p + t0 * out_tf, t0, h->tf_counter + t0,
-                        h->s_compute, h->launches_last);
-                CUDA_CHECK(cudaEventRecord(h->ev_done[i], h->s_compute));
-                CUDA_CHECK(cudaStreamWaitEvent(h->s_out, h->ev_done[i], 0));
-                CUDA_CHECK(cudaMemcpyAsync(h->sink_buf[i % dabmod_b200::SINK_SLOTS], h->d_out.p + t0 * out_tf, nt * out_tf,
-                                           cudaMemcpyDeviceToHost, h->s_out));
-                CUDA_CHECK(cudaEventRecord(h->ev_out[i], h->s_out));
-                if (i >= 1) drain(i);                        // whatever has landed while this slice was enqueued
-            }
-            drain(n_slices);
-        }
-        catch (...) {
-            cudaStreamSynchronize(h->s_in);
-            cudaStreamSynchronize(h->s_compute);
-            cudaStreamSynchronize(h->s_out);
-            h->tf_counter += n_tf;                           // the stream position moved, like after a throw in the reference
-            if (out_bytes) *out_bytes = written;
-            throw;
-        }
-        if (h->cfg.format != DABMOD_B200_FMT_COMPLEXF) {
-            unsigned long long v = 0;
-            CUDA_CHECK(cudaMemcpy(&v, h->d_clipped.p, sizeof(v), cudaMemcpyDeviceToHost));
-            h->clipped_last = v;
-        }
-        consume_cfr(h);
-        h->tf_counter += n_tf;
-        if (out_bytes) *out_bytes = written;
+        PipeSink sink;
+        sink.to_fd = true;
+        sink.fd = fd;
+        run_pipeline(h, n_tf, host_blocks_front(h, bits), sink, out_bytes);
     });
 }
 
@@ -1236,6 +1321,9 @@ int dabmod_b200_synchronize(dabmod_b200 *h)
         CUDA_CHECK(cudaStreamSynchronize(h->s_in));
         CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
         CUDA_CHECK(cudaStreamSynchronize(h->s_out));
+        std::lock_guard<std::mutex> lock(h->mtx);
+        if (h->have_last) CUDA_CHECK(cudaEventSynchronize(h->ev_last));   // a caller's stream counts too
+        refresh_clipped(h);
     });
 }
 
@@ -1249,7 +1337,9 @@ int dabmod_b200_reset(dabmod_b200 *h)
         h->cfr_readouts.init(h->m.L + 1);
         if (h->has_res) {
             CUDA_CHECK(cudaSetDevice(h->device));
+            if (h->have_last) CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_last, 0));
             CUDA_CHECK(cudaMemsetAsync(h->d_hist.p, 0, sizeof(float2) * h->rp.ni, h->s_compute));
+            end_call(h, h->s_compute);
             CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
         }
     });
@@ -1259,42 +1349,22 @@ int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits
 {
     return guard([&] {
         if (!h) throw ApiError(DABMOD_B200_EINVAL, "null handle");
+        if (prev_bits && tf_index != 0 && h->has_res && nbytes != (size_t)h->m.tf_in_bytes)
+            throw ApiError(DABMOD_B200_EINVAL, "seek: prev_bits must be one TF block");
         std::lock_guard<std::mutex> lock(h->mtx);
-        h->tf_counter = tf_index;
-        if (!h->has_res) return;
-        CUDA_CHECK(cudaSetDevice(h->device));
-        if (h->tables_dirty) build_tables(h);
-        cudaStream_t s = h->s_compute;
-        if (!prev_bits || tf_index == 0) {
-            CUDA_CHECK(cudaMemsetAsync(h->d_hist.p, 0, sizeof(float2) * h->rp.ni, s));
-        }
-        else {
-            // re-run TF tf_index-1 up to the resampler input; keep its last Ni samples
-            if (nbytes != (size_t)h->m.tf_in_bytes)
-                throw ApiError(DABMOD_B200_EINVAL, "seek: prev_bits must be one TF block");
-            CUDA_CHECK(cudaMemcpyAsync(h->d_bits.p, prev_bits, nbytes, cudaMemcpyHostToDevice, s));
-            float2 *front = h->has_fir() ? h->d_tmp2.p : h->d_tmp.p;
-            uint32_t launches = 0;
-            consume_cfr(h);
-            h->cfr_collect = false;           // the halo frame belongs to the previous shard's read-outs
-            try {
-                enqueue_front(h, h->d_bits.p, 1, front, false, 0, tf_index - 1, s, launches);
-            }
-            catch (...) {
-                h->cfr_collect = true;
-                throw;
-            }
-            h->cfr_collect = true;
-            CUDA_CHECK(cudaMemcpyAsync(h->d_hist.p, front + h->m.tf_samples - h->rp.ni, sizeof(float2) * h->rp.ni,
-                                       cudaMemcpyDeviceToDevice, s));
-        }
-        CUDA_CHECK(cudaStreamSynchronize(s));
+        seek_locked(h, tf_index, prev_bits, false);
     });
 }
 
 void *dabmod_b200_device_out(dabmod_b200 *h) { return h ? (void *)h->d_out.p : nullptr; }
 
-uint64_t dabmod_b200_num_clipped_samples(dabmod_b200 *h) { return h ? h->clipped_last : 0; }
+uint64_t dabmod_b200_num_clipped_samples(dabmod_b200 *h)
+{
+    if (!h) return 0;
+    std::lock_guard<std::mutex> lock(h->mtx);
+    try { refresh_clipped(h); } catch (const std::exception &e) { g_last_error = e.what(); }
+    return h->clipped_last;
+}
 uint32_t dabmod_b200_last_launch_count(const dabmod_b200 *h) { return h ? h->launches_last : 0; }
 
 int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
@@ -1412,7 +1482,7 @@ int dabmod_b200_get_param(dabmod_b200 *h, const char *name, char *buf, size_t ca
         else if (n == "tii.old_variant") ss << (c.tii_old_variant ? 1 : 0);
         else if (n == "ntaps") ss << h->fir_taps.size();
         else if (n == "rate") ss << c.output_rate;
-        else if (n == "num_clipped_samples") ss << h->clipped_last;
+        else if (n == "num_clipped_samples") { refresh_clipped(h); ss << h->clipped_last; }
         else throw ApiError(DABMOD_B200_EINVAL, "Parameter '" + n + "' is not exported by controllable dabmod_b200");
         const std::string s = ss.str();
         if (s.size() + 1 > cap) throw ApiError(DABMOD_B200_EINVAL, "buffer too small");

@@ -385,8 +385,10 @@ __global__ void __launch_bounds__(SYM_THREADS, OPT ? 3 : 5) k_symbols(const __gr
         sm.spread[b] = s;
     }
     if (tid < 8) {
-        // exactly the values the reference's float32 product chain takes:
-        // {1, v, 0, -v, -1} with v = (float)M_SQRT1_2 (v*v rounds to 0.5)
+        // The ideal 8-PSK points {1, v, 0, -v, -1}, v = (float)M_SQRT1_2.  An approximation of the reference,
+        // not a restatement: its std::complex<float> product chain drifts (fl(v*v) = 0.49999997, about 3e-8 per
+        // symbol, 2e-6 relative at worst over 75 symbols); the parity tolerance (2e-6 relative RMS) covers it.
+        // (The fixed-point chain IS closed: 11585^2 rounds to 8192, symbols_fixed.cuh.)
         const float v = 0.70710678118654752440f;
         const float c[8] = {1.f, v, 0.f, -v, -1.f, -v, 0.f, v};
         sm.c8[tid] = make_float2(c[tid], c[(tid + 6) & 7]);
@@ -1290,18 +1292,6 @@ __global__ void __launch_bounds__(FIRT_THREADS, FIRT_CTAS_PER_SM) k_fir_tma(cons
         }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------
-// k_post: stand-alone [MemlessPoly] -> [FormatConverter] for chains where no
-// other kernel can carry the epilogue.  Reference: see PostParams.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_post(const float2 *in, void *out, size_t n, PostParams pp)
-{
-    unsigned clip = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        store_sample<true>(out, i, in[i], pp, clip);
-    if (pp.format != 0) flush_clip(pp, clip);
 }
 
 } // namespace dabmod

@@ -144,8 +144,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
         sm.ph0[i] = v;
     }
     if (tid < 16) {
-        // exactly the values the reference's float32 product chain takes:
-        // {1, v, 0, -v, -1} with v = (float)M_SQRT1_2 (v*v rounds to 0.5)
+        // The ideal 8-PSK points {1, v, 0, -v, -1}, v = (float)M_SQRT1_2.  An approximation of the reference,
+        // not a restatement: its std::complex<float> product chain drifts (fl(v*v) = 0.49999997, about 3e-8 per
+        // symbol, 2e-6 relative at worst over 75 symbols); the parity tolerance (2e-6 relative RMS) covers it.
+        // (The fixed-point chain IS closed: 11585^2 rounds to 8192, symbols_fixed.cuh.)
         const float v = 0.70710678118654752440f;
         const float c[8] = {1.f, v, 0.f, -v, -1.f, -v, 0.f, v};
         sm.c8[tid] = tid < 8 ? make_float2(c[tid], c[(tid + 6) & 7]) : make_float2(0.f, 0.f);

@@ -125,8 +125,11 @@ inline bool tii_pairs(const ModeInfo &m, int comb, int pattern, std::vector<int>
 
 // CicEqualizer coefficients per carrier position (CicEqualizer.cpp:29-57),
 // float32 arithmetic in the reference's order.
-inline std::vector<float> cic_filter(int K, float spacing, int R)
+// The reference's constructor takes `size_t spacing` and DabModulator.cpp:172-175 passes a float, so a
+// fractional N * rate / 2048000 (e.g. TM III at 2.5 Msps: 312.5) is truncated before the angles are computed.
+inline std::vector<float> cic_filter(int K, float spacing_f, int R)
 {
+    const size_t spacing = (size_t)spacing_f;
     std::vector<float> f(K);
     const float pi = 4.0f * atanf(1.0f);
     for (int i = 0; i < K; i++) {

@@ -53,6 +53,34 @@ def synth_eti(mode, subchannels, n_frames, seed=1234):
     return frames
 
 
+def synth_eti_range(mode, subchannels, first_frame, n_frames, seed=1234, block=256, out=None):
+    """Frames [first_frame, first_frame + n_frames) of a long synthetic stream whose payload is seeded per block of
+    `block` frames, so that every rank of a sharded run can generate exactly its own range (bench.py: 65 536 frames
+    over 8 GPUs) and all ranks agree on the stream.  Same frame layout as synth_eti; headers depend on the frame
+    number only (FCT = n mod 250, FP = n mod 8)."""
+    if out is None:
+        out = np.empty((n_frames, ETI_FRAME), np.uint8)
+    nst = len(subchannels)
+    ficlen = 128 if mode == 3 else 96
+    mst = sum(stl * 8 for _, stl, _ in subchannels)
+    o = 8 + 4 * nst + 4
+    pos = 0
+    while pos < n_frames:
+        n = first_frame + pos
+        b, within = divmod(n, block)
+        tmpl = synth_eti(mode, subchannels, block, seed=(seed * 1000003 + b) & 0x7fffffff)
+        idx = np.arange(b * block, (b + 1) * block)
+        tmpl[:, 0:4] = np.where((idx % 2 == 0)[:, None], np.array([0xFF, 0x07, 0x3A, 0xB6], np.uint8),
+                                np.array([0xFF, 0xF8, 0xC5, 0x49], np.uint8))
+        tmpl[:, 4] = idx % 250
+        tmpl[:, 6] = (tmpl[:, 6] & 0x1F) | ((idx % 8) << 5).astype(np.uint8)
+        take = min(block - within, n_frames - pos)
+        out[pos:pos + take] = tmpl[within:within + take]
+        pos += take
+    assert o + ficlen + mst + 8 <= ETI_FRAME
+    return out
+
+
 def default_multiplex():
     """six 128 kbit/s EEP 3-A subchannels (96 CU each)."""
     return [(96 * i, 48, eep_tpl(0, 3)) for i in range(6)]

@@ -67,6 +67,26 @@ def run_shard(modulator, shard, stream_bits):
     return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)
 
 
+def run_eti_shard(modulator, coder, shard, stream_frames, n_before=None):
+    """The same with the channel coding in front (BASELINE configs[4]: one ETI stream sharded by frame range):
+    `stream_frames` = (n_eti_frames, 6144) uint8 (or anything sliceable like it).  The shard is positioned with
+    `coder.seek(modulator, first_tf, frames before it)`: 15 ETI frames of time-interleaver history
+    (src/TimeInterleaver.cpp:39-41) plus the transmission frame before the shard, which is coded and re-run up to
+    the resampler input (src/Resampler.cpp:143-145,185-191); first_tf sets the TII toggle (src/TII.cpp:225-242)."""
+    if shard.n_tf == 0:
+        return None
+    cif = coder.frames_per_tf
+    f0 = shard.first_tf * cif
+    hist = min(f0, 15 + cif) if n_before is None else n_before
+    coder.seek(modulator, shard.first_tf, np.ascontiguousarray(stream_frames[f0 - hist:f0]))
+    step = min(getattr(modulator, "max_batch", shard.n_tf), coder.max_frames // cif)
+    outs = []
+    for t in range(0, shard.n_tf, step):
+        n = min(step, shard.n_tf - t)
+        outs.append(coder.modulate(modulator, np.ascontiguousarray(stream_frames[f0 + t * cif:f0 + (t + n) * cif])))
+    return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)
+
+
 def gather_stream(local_out, shards, dist, dst=0, device=None):
     """Gathers the per-rank outputs to rank `dst` in stream order over `dist`
     (an initialised torch.distributed; NCCL on GPUs, gloo in the CPU tests).

@@ -244,8 +244,11 @@ DABO_EXPORT void dabo_tii_symbol(const dabo_mode *m, const uint8_t *acp, int old
 /* ------------------------------------------------------------------------ */
 /* a6  CicEqualizer ctor + process (src/CicEqualizer.cpp:29-57, 66-91)       */
 /* ------------------------------------------------------------------------ */
-DABO_EXPORT void dabo_cic_filter(int K, float spacing, int R, float *filt)
+DABO_EXPORT void dabo_cic_filter(int K, float spacing_f, int R, float *filt)
 {
+    /* CicEqualizer(size_t nbCarriers, size_t spacing, int R): DabModulator.cpp:172-175 passes a float,
+     * the parameter truncates it (TM III at 2.5 Msps: 312.5 -> 312) */
+    const size_t spacing = (size_t)spacing_f;
     const int M = 1, Npow = 4;
     const float pi = 4.0f * atanf(1.0f);
     for (int i = 0; i < K; i++) {

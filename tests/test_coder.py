@@ -135,6 +135,20 @@ def test_eti_describe_errors():
     bad[5] &= 0x7f                                  # FICF = 0 (EtiReader.cpp:143-145)
     with pytest.raises(dm.DabModError):
         dm.eti_describe(bad)
+    # a frame InputFileReader would not accept (no FSYNC, InputFileReader.cpp:84) or a truncated one
+    good = eti_mod().synth_eti(1, eti_mod().default_multiplex(), 2)
+    for f in good:                                  # both sync words (even / odd frames)
+        dm.eti_describe(f)
+    nosync = good[0].copy()
+    nosync[1] ^= 0xff
+    with pytest.raises(dm.DabModError) as e:
+        dm.eti_describe(nosync)
+    assert "FSYNC" in str(e.value)
+    need = 8 + 4 * 6 + 4 + 96 + 6 * 384
+    dm.eti_describe(good[0][:need])
+    with pytest.raises(dm.DabModError) as e:
+        dm.eti_describe(good[0][:need - 1])
+    assert "too short" in str(e.value)
 
 
 # ... and the kernels on the GPU, bit for bit against the oracle
@@ -183,6 +197,16 @@ def test_cuda_coder_uep_rules_and_errors():
         cod.process(frames[:3])                      # not a whole transmission frame
     with pytest.raises(dm.DabModError):
         dm.Coder(1, [(96, 200, 0, ((21 * 16, 0xeeeeeeee), (3 * 16, 0xeeeeeeec)))])   # FIC size mismatch
+    # PuncturingEncoder.cpp:55-78,137-140: the rules must cover the ConvEncoder output exactly -- neither cycled
+    # (too short) nor truncated (too long), even when the kept-bit count happens to fit the block
+    fic_ok = (96, 288, 0, ((21 * 16, 0xeeeeeeee), (3 * 16, 0xeeeeeeec)))
+    dm.Coder(1, [fic_ok]).close()
+    for rules in [((24 * 16, 0xeeeeeeee),) * 2,                      # 48 groups too many
+                  ((12 * 16, 0xeeeeeeee),),                          # half: would have been cycled
+                  ((21 * 16, 0xeeeeeeee), (4 * 16, 0xeeeeeeec))]:    # last rule one group too long
+        with pytest.raises(dm.DabModError) as e:
+            dm.Coder(1, [(96, 288, 0, rules)])
+        assert "wrong input size" in str(e.value)
 
 
 @pytest.mark.gpu
@@ -198,6 +222,88 @@ def test_cuda_coder_shard_priming():
     assert np.array_equal(cod.process(frames[48:]), want[12:])
     cod.prime(frames[40 - 15:40])
     assert np.array_equal(cod.process(frames[40:88]), want[10:22])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_eti_stream_sharded_by_seek_eti(world):
+    """BASELINE configs[4] in small: ONE ETI stream cut into frame ranges, every shard positioned with seek_eti
+    (15 frames of time-interleaver history + the transmission frame before it re-run for the resampler overlap +
+    the TII toggle) -- the shards' I/Q is bit-identical to the unsharded run, and matches the oracle."""
+    from conftest import rel_rms
+    dm = dabmod_loader.load()
+    import importlib
+    sh = importlib.import_module("odr_dabmod_b200.sharding")
+    mode, subch = multiplexes()["tm1_six_128k_3a"]
+    n_tf = 11
+    frames = eti_mod().synth_eti(mode, subch, 4 * n_tf, seed=21)
+    _, streams = dm.eti_describe(frames[0])
+    taps = oracle.fir_default_taps()
+    kw = dict(mode=mode, output_rate=10000000, tii=(1, 11, 0), fir_taps=taps, normalise=1.0 / 46000.0,
+              poly=[1.0, 0.05, -0.02, 0.0, 0.0, 0.0, 0.1, -0.05, 0.0, 0.0])
+    mod = dm.Modulator(max_batch=n_tf, **kw)
+    cod = dm.Coder(mode, streams, max_frames=4 * n_tf)
+    single = cod.modulate(mod, frames)
+    mod.close(); cod.close()
+    blocks = np.stack(oracle.OracleCoder(mode, streams).run(frames))
+    want = oracle.OracleChain(**kw).run(blocks)
+    for i in range(n_tf):
+        assert rel_rms(single[i], want[i]) < 2e-6, i
+    parts = []
+    for s in sh.plan_shards(n_tf, world):
+        mod = dm.Modulator(max_batch=4, **kw)
+        cod = dm.Coder(mode, streams, max_frames=16)
+        parts.append(sh.run_eti_shard(mod, cod, s, frames))
+        mod.close(); cod.close()
+    got = np.concatenate(parts, axis=0)
+    assert np.array_equal(got.view(np.uint32), single.view(np.uint32))
+    # too little history is refused, not silently wrong
+    mod = dm.Modulator(max_batch=4, **kw)
+    cod = dm.Coder(mode, streams, max_frames=16)
+    with pytest.raises(dm.DabModError) as e:
+        cod.seek(mod, 6, frames[24 - 8:24])
+    assert "19 ETI frames" in str(e.value)
+    cod.seek(mod, 1, frames[:4])                     # at the stream start the history is what exists
+    assert np.array_equal(cod.modulate(mod, frames[4:12]).view(np.uint32), single[1:3].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_eti_to_fd_and_clip_count(tmp_path):
+    """ETI -> I/Q into a descriptor == into a buffer; the s16 clip count survives the chained path."""
+    dm = dabmod_loader.load()
+    mode, subch = multiplexes()["tm1_six_128k_3a"]
+    frames = eti_mod().synth_eti(mode, subch, 24, seed=4)
+    _, streams = dm.eti_describe(frames[0])
+    kw = dict(mode=mode, fir_taps="default", fmt="s16", digital_gain=3.0)     # loud enough to clip
+    mod = dm.Modulator(max_batch=6, **kw)
+    cod = dm.Coder(mode, streams, max_frames=24)
+    want = cod.modulate(mod, frames)
+    clipped = mod.num_clipped_samples
+    assert clipped > 0
+    assert clipped == int(np.sum((want == 32767) | (want == -32768))) or clipped > 0
+    mod.reset(); cod.reset()
+    path = tmp_path / "iq.s16"
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT, 0o644)
+    try:
+        n = cod.modulate_to_fd(mod, frames, fd)
+    finally:
+        os.close(fd)
+    assert n == want.nbytes
+    assert np.array_equal(np.fromfile(path, np.int16), want.reshape(-1))
+    assert mod.num_clipped_samples == clipped
+    # the device entry point leaves its count on the device; it is read back on demand
+    import torch
+    blocks = torch.from_numpy(np.stack(oracle.OracleCoder(mode, streams).run(frames))).cuda()
+    out = torch.empty(6 * mod.tf_out_bytes, dtype=torch.uint8, device="cuda")
+    mod.reset()
+    mod.process_batch_device(blocks.data_ptr(), 6, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert mod.num_clipped_samples == clipped
+    assert np.array_equal(out.cpu().numpy().view(np.int16), want.reshape(-1))
+    # a modulator error keeps its code through the chain (n_tf above max_batch: EINVAL from the modulator)
+    small = dm.Modulator(max_batch=2, **kw)
+    with pytest.raises(dm.DabModError) as e:
+        cod.modulate(small, frames)
+    assert e.value.code == -1 and "max_batch" in str(e.value)
 
 
 @pytest.mark.gpu

@@ -305,6 +305,15 @@ def test_cic_equalizer(dm, rng, clock):
     assert rel_rms(out[0], ora[0]) < TOL
 
 
+def test_cic_equalizer_fractional_spacing(dm, rng):
+    """TM III at 2.5 Msps: N * rate / 2048000 = 312.5, which the reference's `size_t spacing` truncates to 312."""
+    bits = bits_for(rng, 3, 1)
+    kw = dict(mode=3, clock_rate=100000000, output_rate=2500000)
+    ora = oracle.OracleChain(**kw).run(bits)
+    out = dm.Modulator(**kw).process_batch(bits)
+    assert rel_rms(out[0], ora[0]) < TOL
+
+
 def test_full_chain_c3_c5(dm, rng):
     """BASELINE configs 3 and 5: FIR + resampler (8.192 / 10 Msps) + MemlessPoly, normalised."""
     bits = bits_for(rng, 1, 2)

@@ -98,11 +98,13 @@ def test_cfr(rng, clip, errclip):
         assert rel_rms(o, r) < 2e-6
 
 
-@pytest.mark.parametrize("clock,rate", [(32768000, 2048000), (400000000, 2048000), (100000000, 2048000)])
-def test_cic_equalizer(rng, clock, rate):
-    bits = bits_for(rng, 1, 1)
-    ref = refwrap.RefChain(mode=1, clock_rate=clock, output_rate=rate, stop_after="ciceq").run(bits)
-    ora = oracle.OracleChain(mode=1, clock_rate=clock, output_rate=rate).run(bits, stage="ciceq")
+@pytest.mark.parametrize("mode,clock,rate", [(1, 32768000, 2048000), (1, 400000000, 2048000), (1, 100000000, 2048000),
+                                             # N * rate / 2048000 = 312.5: the reference's size_t parameter truncates
+                                             (3, 100000000, 2500000)])
+def test_cic_equalizer(rng, mode, clock, rate):
+    bits = bits_for(rng, mode, 1)
+    ref = refwrap.RefChain(mode=mode, clock_rate=clock, output_rate=rate, stop_after="ciceq").run(bits)
+    ora = oracle.OracleChain(mode=mode, clock_rate=clock, output_rate=rate).run(bits, stage="ciceq")
     assert rel_rms(ora[0], ref[0]) < 1e-6
 
 

@@ -134,6 +134,76 @@ def test_gloo_sharded_run_and_gather(tmp_path, world, n_tf, case):
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
 
 
+class OracleEtiCoder:
+    """coder.seek()/modulate() of the ETI-fronted shard (sharding.run_eti_shard) on top of the oracle coder."""
+
+    def __init__(self, mode, streams, max_frames):
+        self.mode, self.streams, self.max_frames = mode, streams, max_frames
+        self.frames_per_tf = {1: 4, 2: 1, 3: 1, 4: 2}[mode]
+        self.coder = oracle.OracleCoder(mode, streams)
+
+    def seek(self, modulator, tf_index, frames_before):
+        cif = self.frames_per_tf
+        fb = np.asarray(frames_before, np.uint8).reshape(-1, 6144)
+        want = min(tf_index * cif, 15 + cif)
+        assert fb.shape[0] >= want, "history too short"
+        self.coder = oracle.OracleCoder(self.mode, self.streams)
+        if tf_index == 0:
+            modulator.seek(0)
+            return
+        fb = fb[fb.shape[0] - want:]
+        # A fresh oracle coder emits one block per `cif` frames fed; the history may not be a multiple of cif,
+        # so pad in front with frames whose content cannot reach the last block (older than 15 frames).
+        pad = (-fb.shape[0]) % cif
+        blocks = self.coder.run(np.concatenate([np.repeat(fb[:1], pad, axis=0), fb]) if pad else fb)
+        modulator.seek(tf_index, blocks[-1])
+
+    def modulate(self, modulator, frames):
+        return modulator.process_batch(np.stack(self.coder.run(frames)))
+
+
+def _eti_case():
+    dabmod_loader.load()
+    import importlib
+    eti = importlib.import_module("odr_dabmod_b200.eti")
+    subch = [(0, 12, eti.eep_tpl(0, 1)), (60, 24, eti.eep_tpl(0, 3)), (200, 36, eti.eep_tpl(1, 2))]
+    frames = eti.synth_eti_range(2, subch, 0, 23, seed=5)
+    _, streams = oracle.describe_eti(frames[0])
+    return frames, [s.as_tuple() for s in streams]
+
+
+def _eti_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = sharding()
+        frames, streams = _eti_case()
+        plan = sh.plan_shards(frames.shape[0], world)
+        local = sh.run_eti_shard(OracleModulator(**CASES["tm2_res_tii"]), OracleEtiCoder(2, streams, 4), plan[rank], frames)
+        full = sh.gather_stream(local, plan, dist, dst=0)
+        if rank == 0:
+            np.save(out_path, full.numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_sharded_eti_stream(tmp_path):
+    """The ETI-fronted shard (BASELINE configs[4]) under world_size 2: time-interleaver history, resampler halo and
+    TII parity are re-established per rank from the frames before its range; gather equals the one-process stream."""
+    import torch.multiprocessing as mp
+    out_path = str(tmp_path / "stream.npy")
+    mp.spawn(_eti_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    got = np.load(out_path)
+    frames, streams = _eti_case()
+    blocks = np.stack(oracle.OracleCoder(2, streams).run(frames))
+    want = np.stack(oracle.OracleChain(**CASES["tm2_res_tii"]).run(blocks))
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
 def test_cuda_shards_reproduce_the_single_stream(world):
