@@ -582,6 +582,51 @@ def measure_sharded_stream(dm, torch, dist, rank, world, local_rank, n_eti_frame
 
 
 
+def measure_pcie_ceiling(torch, dist, world, nbytes=1 << 30, reps=6):
+    """The denominator of every host-delivered number: raw cudaMemcpyAsync between pinned host memory and HBM, no
+    kernels, all ranks at once (the host's memory system and PCIe root complexes are shared by the GPUs of a box).
+    Returns aggregate GB/s in both directions and with both running together."""
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    host2 = torch.empty(nbytes // 8, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dev2 = torch.empty(nbytes // 8, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def d2h():
+        with torch.cuda.stream(s1):
+            host.copy_(dev, non_blocking=True)
+
+    def h2d():
+        with torch.cuda.stream(s2):
+            dev.copy_(host, non_blocking=True)
+
+    def both():                                  # the shape of the pipeline: a big D2H stream, a small H2D stream
+        with torch.cuda.stream(s1):
+            host.copy_(dev, non_blocking=True)
+        with torch.cuda.stream(s2):
+            dev2.copy_(host2, non_blocking=True)
+
+    t_d2h, t_h2d, t_both = timed(d2h), timed(h2d), timed(both)
+    gb = world * nbytes * reps / 1e9
+    return {"ranks": world, "bytes_per_copy": nbytes, "copies": reps,
+            "d2h_GB/s": gb / t_d2h, "h2d_GB/s": gb / t_h2d, "d2h_with_small_h2d_GB/s": gb / t_both,
+            "how": "cudaMemcpyAsync pinned<->HBM on every rank at once, wall clock, max over ranks, no kernels"}
+
+
 def bind_to_gpu_numa_node(gpu_index):
     """Run this rank (and allocate its pinned host buffers) on the CPUs next to its GPU: the end-to-end leg
     moves 1.6 GB per step over PCIe, and a remote NUMA node costs a third of that bandwidth."""
@@ -706,6 +751,13 @@ def gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     checksum = int(host_out[::65537].to(torch.int64).sum().item())  # the D2H result is read (strided over the whole buffer)
 
+    # ---- the host's PCIe ceiling with every rank copying at once (denominator of the host-delivered numbers) ----
+    pcie = None
+    try:
+        pcie = measure_pcie_ceiling(torch, dist, world)
+    except Exception as e:
+        pcie = {"error": "%s: %s" % (type(e).__name__, e)}
+
     # ---- BASELINE configs[4]: one ETI stream sharded across the ranks (every rank takes part) ----
     sharded = None
     if args.stream_frames > 0:
@@ -792,12 +844,20 @@ def gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": "ETI frames/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "checksum": checksum,
                 "d2h_GB/s": world * out_bytes * e2e_steps / e2e_s / 1e9,
-                "bound": "PCIe: 1.57 MB of complexf per TF through one x16 link"},
+                "pcie_ceiling": pcie,
+                "frac_of_d2h_ceiling": (world * out_bytes * e2e_steps / e2e_s / 1e9 / pcie["d2h_GB/s"]
+                                        if pcie and "d2h_GB/s" in pcie else None),
+                "bound": "PCIe: 1.57 MB of complexf per TF through one x16 link; with several GPUs the host side "
+                         "(memory system, root complexes) all ranks share"},
         "gpu_launches": launches,
         "roofline": roofline,
         "clocks": clocks,
     }
     if sharded is not None:
+        if pcie and "d2h_GB/s" in pcie:
+            for k in ("host_delivered_complexf", "host_delivered_s16"):
+                if k in sharded:
+                    sharded[k]["frac_of_d2h_ceiling"] = sharded[k]["d2h_GB/s"] / pcie["d2h_GB/s"]
         line["sharded_stream"] = sharded
         line["config"]["sharded_stream_workload"] = STREAM_WORKLOAD
     if cpu is not None:

@@ -232,6 +232,8 @@ struct dabmod_b200 {
     bool res_up = false;           // k_resample_up applies (Ni = 4096, integer ratio <= 4)
     bool res_q = false;            // k_resample_q applies (Ni = 4096, No = P * 4000, P = 2..5)
     bool allow_res_up = true;      // "res_kernel" knob: 0 = always the generic kernel
+    int res_kernel = 1;            //   2 = the older variant of a fast kernel where two exist
+    int res_dbg = 0;               // "res_dbg": profiling aid, skips parts of the resampler kernels (wrong results)
     size_t res_smem = 0;
 
     uint64_t clipped_last = 0;
@@ -668,11 +670,33 @@ void enqueue_resampler(dabmod_b200 *h, const float2 *in, size_t n_tf, void *d_ou
     p.scratch = h->res_smem ? nullptr : h->d_scratch.p;
     p.out = d_out;
     p.post = make_post(h, post);
+    p.dbg = h->res_dbg;
     if (h->res_up && h->allow_res_up) {
         // TM I, integer up-sampling: L transforms of Ni points per hop, all in shared memory
         RuParams pu{};
         pu.r = p;
         pu.L = (int)rp.L;
+        if (h->res_kernel != 2) {
+            // three teams per SM (resample_up.cuh); "res_kernel" = 2 keeps the two-team kernel with output staging
+            const int grid3 = (int)std::min<long long>((p.total_hops + RU3_TEAMS - 1) / RU3_TEAMS, h->sm_count);
+            ProfScope prof3(h, "k_resample_up3", s);
+            auto go = [&](auto kern) {
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ru3Smem)));
+                kern<<<grid3, RU3_THREADS, sizeof(Ru3Smem), s>>>(pu);
+            };
+            switch (pu.L * 2 + (post ? 1 : 0)) {
+                case 4: go(k_resample_up3<false, 2>); break;
+                case 5: go(k_resample_up3<true, 2>); break;
+                case 6: go(k_resample_up3<false, 3>); break;
+                case 7: go(k_resample_up3<true, 3>); break;
+                case 8: go(k_resample_up3<false, 4>); break;
+                default: go(k_resample_up3<true, 4>); break;
+            }
+            CUDA_CHECK(cudaGetLastError());
+            prof3.end();
+            launches++;
+        }
+        else {
         const int grid = (int)std::min<long long>((p.total_hops + RU_TEAMS - 1) / RU_TEAMS, h->sm_count);
         ProfScope prof(h, "k_resample_up", s);
         if (post) {
@@ -688,6 +712,7 @@ void enqueue_resampler(dabmod_b200 *h, const float2 *in, size_t n_tf, void *d_ou
         CUDA_CHECK(cudaGetLastError());
         prof.end();
         launches++;
+        }
     }
     else if (h->res_q && h->allow_res_up) {
         // TM I, No = P * 4000 (4 / 6 / 8 / 10 Msps): P phase transforms of 4000 points per hop in shared memory
@@ -1391,7 +1416,8 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             else if (n == "sym_chunks") { int v; ss >> v; h->force_chunks = v < 0 ? 0 : v; }
             else if (n == "sym_kernel") { int v; ss >> v; h->use_warp_kernel = v != 0; }
             else if (n == "fir_kernel") { int v; ss >> v; h->use_fir_sym = v != 0; h->fir_kernel = v; }
-            else if (n == "res_kernel") { int v; ss >> v; h->allow_res_up = v != 0; }
+            else if (n == "res_kernel") { int v; ss >> v; h->allow_res_up = v != 0; h->res_kernel = v; }
+            else if (n == "res_dbg") { int v; ss >> v; h->res_dbg = v; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {
                 std::string v; ss >> v;

@@ -41,6 +41,8 @@ struct ResParams {
     float2 *scratch;               // gridDim.x * 2 * max(ni, no) entries, or nullptr = shared memory
     void *out;                     // total_hops * ho samples
     PostParams post;
+    int dbg;                       // profiling aid ("res_dbg", results are WRONG when non-zero): 1 no input loads,
+                                   // 2 no stores, 4 no inverse transforms, 8 no forward transform
 };
 
 __device__ __forceinline__ float2 res_load(const ResParams &p, long long s)
