@@ -2,6 +2,7 @@
  * kernels behind dabmod_b200_process(). */
 #include "B200OfdmChain.h"
 
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -66,9 +67,13 @@ int load_coefs(const std::string& file, std::vector<float>& coefs)
 
 } // namespace
 
-B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format, int device, bool fixedPoint) :
+B200OfdmChain::B200OfdmChain(mod_settings_t& s, const std::string& format, int device, bool fixedPoint,
+                             int pipelineDepth) :
     ModCodec(),
-    RemoteControllable("b200chain")
+    RemoteControllable("b200chain"),
+    m_settings(s),
+    m_tii(*this),
+    m_depth(pipelineDepth > 0 ? (size_t)pipelineDepth : 0)
 {
     dabmod_b200_config c;
     dabmod_b200_config_init(&c);
@@ -106,9 +111,13 @@ B200OfdmChain::B200OfdmChain(const mod_settings_t& s, const std::string& format,
     else if (format == "u8") c.format = DABMOD_B200_FMT_U8;
     else if (format == "s8") c.format = DABMOD_B200_FMT_S8;
     else throw std::runtime_error("FormatConverter: Invalid format " + format);
-    c.max_batch = 1;
+    c.max_batch = m_depth > 0 ? (int32_t)m_depth : 1;
 
     if (dabmod_b200_create(&c, &m_handle) != DABMOD_B200_OK) fail("create");
+    if (m_depth > 0) {
+        m_in.resize(m_depth * dabmod_b200_tf_in_bytes(m_handle));
+        m_ready.resize(m_depth * dabmod_b200_tf_out_bytes(m_handle));
+    }
 
     /* names of the replaced blocks' parameters (GainControl.cpp:520-603, TII.cpp:339-376,
      * OfdmGenerator.cpp:63-67, GuardIntervalInserter.cpp:100-103) */
@@ -144,13 +153,47 @@ int B200OfdmChain::process(Buffer* const dataIn, Buffer* dataOut)
         throw std::runtime_error("B200OfdmChain::process input size not valid: " +
                                  std::to_string(dataIn->getLength()));
     }
-    dataOut->setLength(dabmod_b200_tf_out_bytes(m_handle));
+    const size_t in_tf = dabmod_b200_tf_in_bytes(m_handle), out_tf = dabmod_b200_tf_out_bytes(m_handle);
+    dataOut->setLength(out_tf);
+    if (m_depth > 0) {
+        /* call i: TF i in, TF i - D out; every D-th call turns the D collected TFs into one batch */
+        const size_t slot = m_calls % m_depth;
+        const bool primed = m_calls >= m_depth;
+        if (primed) memcpy(dataOut->getData(), m_ready.data() + slot * out_tf, out_tf);
+        /* before the first result: an empty buffer and 0, which ends this flowgraph iteration
+         * (src/Flowgraph.cpp:331-336) -- what a PipelinedModCodec's first call amounts to (its input was
+         * swapped away before the output is sized from it, src/ModPlugin.cpp:96-109) */
+        else dataOut->setLength(0);
+        memcpy(m_in.data() + slot * in_tf, dataIn->getData(), in_tf);
+        m_calls++;
+        if (slot == m_depth - 1) {
+            size_t nb = 0;
+            if (dabmod_b200_process_batch(m_handle, m_in.data(), m_depth, m_ready.data(), m_ready.size(), &nb) !=
+                DABMOD_B200_OK) {
+                fail("process_batch");
+            }
+        }
+        return primed ? (int)out_tf : 0;
+    }
     size_t n = 0;
     if (dabmod_b200_process(m_handle, reinterpret_cast<const uint8_t*>(dataIn->getData()), dataIn->getLength(),
                             dataOut->getData(), dataOut->getLength(), &n) != DABMOD_B200_OK) {
         fail("process");
     }
     return (int)n;
+}
+
+meta_vec_t B200OfdmChain::process_metadata(const meta_vec_t& metadataIn)
+{
+    if (m_depth == 0) return metadataIn;
+    /* PipelinedModCodec::process_metadata (src/ModPlugin.cpp:117-128) with a FIFO of D + 1 instead of 2 */
+    m_metadata_fifo.push_back(metadataIn);
+    if (m_metadata_fifo.size() == m_depth + 1) {
+        auto r = std::move(m_metadata_fifo.front());
+        m_metadata_fifo.pop_front();
+        return r;
+    }
+    return {};
 }
 
 size_t B200OfdmChain::get_num_clipped_samples() const
@@ -163,6 +206,52 @@ void B200OfdmChain::set_parameter(const std::string& parameter, const std::strin
     if (dabmod_b200_set_param(m_handle, parameter.c_str(), value.c_str()) != DABMOD_B200_OK) {
         throw ParameterError(dabmod_b200_last_error());
     }
+    write_back(parameter);
+}
+
+/* the accepted value goes into DabModulator's settings, where a rebuilt chain will find it */
+void B200OfdmChain::write_back(const std::string& parameter)
+{
+    const std::string v = get_parameter(parameter);
+    std::stringstream ss(v);
+    if (parameter == "digital") ss >> m_settings.digitalgain;
+    else if (parameter == "var") ss >> m_settings.gainmodeVariance;
+    else if (parameter == "mode")
+        m_settings.gainMode = v == "fix" ? GainMode::GAIN_FIX : v == "max" ? GainMode::GAIN_MAX : GainMode::GAIN_VAR;
+    else if (parameter == "windowlen") ss >> m_settings.ofdmWindowOverlap;
+    else if (parameter == "cfr") { int b = 0; ss >> b; m_settings.enableCfr = b != 0; }
+    else if (parameter == "clip") ss >> m_settings.cfrClip;
+    else if (parameter == "errorclip") ss >> m_settings.cfrErrorClip;
+    else if (parameter == "tii.enable") { int b = 0; ss >> b; m_settings.tiiConfig.enable = b != 0; }
+    else if (parameter == "tii.comb") ss >> m_settings.tiiConfig.comb;
+    else if (parameter == "tii.pattern") ss >> m_settings.tiiConfig.pattern;
+    else if (parameter == "tii.old_variant") { int b = 0; ss >> b; m_settings.tiiConfig.old_variant = b != 0; }
+}
+
+B200TiiControl::B200TiiControl(B200OfdmChain& chain) : RemoteControllable("tii"), m_chain(chain)
+{
+    /* src/TII.cpp:120-127 */
+    m_parameters.push_back({"enable", "enable TII [0-1]"});
+    m_parameters.push_back({"comb", "TII comb number [0-23]"});
+    m_parameters.push_back({"pattern", "TII pattern number [0-69]"});
+    m_parameters.push_back({"old_variant", "select old TII variant for old (buggy) receivers: 0 = off, 1 = on"});
+}
+
+void B200TiiControl::set_parameter(const std::string& parameter, const std::string& value)
+{
+    m_chain.set_parameter("tii." + parameter, value);
+}
+
+const std::string B200TiiControl::get_parameter(const std::string& parameter) const
+{
+    return m_chain.get_parameter("tii." + parameter);
+}
+
+const json::map_t B200TiiControl::get_all_values() const
+{
+    json::map_t map;
+    for (const char* p : {"enable", "comb", "pattern", "old_variant"}) map[p].v = get_parameter(p);
+    return map;
 }
 
 const std::string B200OfdmChain::get_parameter(const std::string& parameter) const
@@ -177,7 +266,8 @@ const std::string B200OfdmChain::get_parameter(const std::string& parameter) con
 const json::map_t B200OfdmChain::get_all_values() const
 {
     json::map_t map;
-    for (const char* p : {"digital", "mode", "var", "tii.enable", "tii.comb", "tii.pattern", "tii.old_variant"}) {
+    for (const char* p : {"digital", "mode", "var", "tii.enable", "tii.comb", "tii.pattern", "tii.old_variant",
+                          "windowlen", "cfr", "clip", "errorclip", "clip_stats", "papr"}) {
         map[p].v = get_parameter(p);
     }
     return map;

@@ -53,10 +53,21 @@ struct ref_cfg {          /* same layout as oracle/ref_harness.cpp */
 
 namespace {
 
-class BitsInput : public ModInput {
+class BitsInput : public ModInput, public ModMetadata {
 public:
     const uint8_t *data = nullptr;
     size_t len = 0;
+    int32_t calls = 0;
+    /* one timestamp per call, numbered by the call: what EtiReader's metadata looks like to the chain */
+    meta_vec_t process_metadata(const meta_vec_t &) override
+    {
+        flowgraph_metadata md;
+        md.ts.fct = calls++;
+        md.ts.fp = 0;
+        md.ts.timestamp_sec = 0;
+        md.ts.timestamp_pps = 0;
+        return {md};
+    }
     int process(Buffer *dataOut) override
     {
         dataOut->setData(data, len);
@@ -70,6 +81,7 @@ struct Harness {
     Buffer out;
     std::shared_ptr<BitsInput> input;
     std::shared_ptr<B200OfdmChain> chain;
+    std::shared_ptr<OutputMemory> output;
     std::unique_ptr<Flowgraph> fg;
 };
 
@@ -81,7 +93,11 @@ extern "C" {
 
 const char *adp_last_error(void) { return g_err.c_str(); }
 
-void *adp_create(const ref_cfg *c, int device)
+void *adp_create2(const ref_cfg *c, int device, int depth);
+void *adp_create(const ref_cfg *c, int device) { return adp_create2(c, device, 0); }
+
+/* depth > 0: the adapter's N-TF pipeline (call i returns TF i - depth, metadata delayed alike) */
+void *adp_create2(const ref_cfg *c, int device, int depth)
 {
     try {
         auto h = std::make_unique<Harness>();
@@ -108,10 +124,10 @@ void *adp_create(const ref_cfg *c, int device)
 
         h->fg = std::make_unique<Flowgraph>(false);
         h->input = std::make_shared<BitsInput>();
-        h->chain = std::make_shared<B200OfdmChain>(s, c->format ? c->format : "", device);
-        auto output = std::make_shared<OutputMemory>(&h->out);
+        h->chain = std::make_shared<B200OfdmChain>(s, c->format ? c->format : "", device, false, depth);
+        h->output = std::make_shared<OutputMemory>(&h->out);
         h->fg->connect(h->input, h->chain);
-        h->fg->connect(h->chain, output);
+        h->fg->connect(h->chain, h->output);
         return h.release();
     }
     catch (const std::exception &e) {
@@ -167,6 +183,46 @@ int adp_get_parameter(void *hp, const char *name, char *buf, size_t cap)
         g_err = e.what();
         return -1;
     }
+}
+
+/* frame count of the timestamp that reached OutputMemory with the last run (-1: none) */
+int adp_last_metadata_fct(void *hp)
+{
+    const auto md = static_cast<Harness *>(hp)->output->get_latest_metadata();
+    return md.empty() ? -1 : md.front().ts.fct;
+}
+
+/* the reference's separate "tii" controllable (src/TII.cpp:106-127) as the adapter exposes it */
+int adp_tii_set(void *hp, const char *name, const char *value)
+{
+    try {
+        auto rc = static_cast<Harness *>(hp)->chain->tii_control();
+        if (rc->get_rc_name() != "tii") throw std::runtime_error("controllable is not named tii");
+        rc->set_parameter(name, value);
+        return 0;
+    }
+    catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+/* a field of the mod_settings_t the chain was built from: remote-control changes must land there */
+double adp_setting(void *hp, const char *name)
+{
+    const mod_settings_t &s = static_cast<Harness *>(hp)->s;
+    const std::string n(name);
+    if (n == "digital") return s.digitalgain;
+    if (n == "var") return s.gainmodeVariance;
+    if (n == "mode") return (double)(int)s.gainMode;
+    if (n == "windowlen") return (double)s.ofdmWindowOverlap;
+    if (n == "cfr") return s.enableCfr;
+    if (n == "clip") return s.cfrClip;
+    if (n == "errorclip") return s.cfrErrorClip;
+    if (n == "tii.enable") return s.tiiConfig.enable;
+    if (n == "tii.comb") return s.tiiConfig.comb;
+    if (n == "tii.pattern") return s.tiiConfig.pattern;
+    return -1e9;
 }
 
 void adp_destroy(void *hp) { delete static_cast<Harness *>(hp); }

@@ -1,0 +1,151 @@
+"""The accelerated engine inside the real program.
+
+oracle/_ref/odr-dabmod-ref  = the complete reference program, every source unmodified (FFTW behind the KISS shim).
+oracle/_ref/odr-dabmod-b200 = the same program with `modulator.fft_engine = b200 | b200_fixed`: patched copies of
+ConfigParser.cpp / DabModulator.cpp / DabMod.cpp (oracle/patch_engine.py; headers untouched) + the product's adapter.
+Both read the same ETI(NI) file through InputFileReader -> EtiReader -> the reference's own channel coding graph and
+write an I/Q file through OutputFile; only the chain behind BlockPartitioner differs.  The files must agree TF by TF
+(the reference never flushes its P pipelined stages, so its file is P transmission frames shorter).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import dabmod_loader  # noqa: E402
+from conftest import rel_rms, write_poly_file  # noqa: E402
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "odr-dabmod-ref")
+B200_BIN = os.path.join(ROOT, "oracle", "_ref", "odr-dabmod-b200")
+have = os.path.exists(REF_BIN) and os.path.exists(B200_BIN)
+
+INI = """[remotecontrol]
+zmqctrl=0
+telnet=0
+[log]
+syslog=0
+[input]
+transport=file
+source={eti}
+loop=0
+[modulator]
+fft_engine={engine}
+gainmode={gainmode}
+mode={mode}
+rate={rate}
+digital_gain={digital_gain}
+{modulator_extra}
+[firfilter]
+enabled={fir}
+[poly]
+enabled={poly}
+polycoeffile={polyfile}
+num_threads=1
+[tii]
+enable={tii}
+comb=3
+pattern=20
+[output]
+output=file
+[fileoutput]
+format={fmt}
+filename={out}
+"""
+
+
+def eti_mod():
+    dabmod_loader.load()
+    import importlib
+    return importlib.import_module("odr_dabmod_b200.eti")
+
+
+def run_binary(binary, tmp_path, tag, eti_path, engine, depth=0, **kw):
+    cfg = dict(mode=1, rate=2048000, gainmode="var", digital_gain=1.0, fir=0, poly=0, polyfile="/dev/null", tii=0,
+               fmt="complexf", modulator_extra="")
+    cfg.update(kw)
+    out = str(tmp_path / ("out_%s.iq" % tag))
+    ini = str(tmp_path / ("cfg_%s.ini" % tag))
+    with open(ini, "w") as f:
+        f.write(INI.format(eti=eti_path, engine=engine, out=out, **cfg))
+    env = dict(os.environ)
+    env["ODR_DABMOD_B200_DEPTH"] = str(depth)
+    r = subprocess.run([binary, ini], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    return out
+
+
+def make_eti(tmp_path, mode, n_tf, seed=3):
+    e = eti_mod()
+    cif = {1: 4, 2: 1, 3: 1, 4: 2}[mode]
+    subch = e.default_multiplex() if mode == 1 else [(0, 12, e.eep_tpl(0, 1)), (60, 24, e.eep_tpl(0, 3))]
+    frames = e.synth_eti_range(mode, subch, 0, n_tf * cif, seed=seed)
+    path = str(tmp_path / "in.eti")
+    frames.tofile(path)
+    return path
+
+
+@pytest.mark.skipif(not have, reason="oracle/_ref binaries not built (make -C oracle binary)")
+def test_reference_binary_matches_the_reference_harness(tmp_path):
+    """CPU: the complete unmodified program and the hot-path harness (oracle/ref_harness.cpp, the checker of every
+    parity test) produce the same bytes, so the harness IS the program's chain."""
+    from oracle import oracle, refwrap
+    if not refwrap.available():
+        pytest.skip("reference library not built")
+    eti_path = make_eti(tmp_path, 1, 6)
+    out = run_binary(REF_BIN, tmp_path, "ref", eti_path, "fftw", fir=1)
+    got = np.fromfile(out, np.complex64).reshape(-1, 196608)
+    frames = np.fromfile(eti_path, np.uint8).reshape(-1, 6144)
+    mode, streams = oracle.describe_eti(frames[0])
+    blocks = np.stack(oracle.OracleCoder(mode, [s.as_tuple() for s in streams]).run(frames))
+    want = refwrap.RefChain(mode=1, fir_taps_file="default").run(blocks)
+    assert got.shape[0] == 6 - 2                      # GainControl and FIRFilter are pipelined: 2 TFs never flushed
+    for i in range(got.shape[0]):
+        assert np.array_equal(got[i].view(np.uint32), want[i].view(np.uint32)), i
+
+
+CASES = {
+    # name: (mode, n_tf, reference engine, b200 engine, dtype, pipelined stages of the reference, ini settings)
+    "c1_native": (1, 6, "fftw", "b200", np.complex64, 1, dict()),
+    "c2_fir": (1, 6, "fftw", "b200", np.complex64, 2, dict(fir=1)),
+    "c3_fir_res_poly": (1, 5, "fftw", "b200", np.complex64, 3, dict(fir=1, rate=8192000, poly=1, fmt="complexf_normalised")),
+    "tm2_s16_tii": (2, 12, "fftw", "b200", np.int16, 1, dict(mode=2, fmt="s16", tii=1, digital_gain=0.8)),
+    "fixed_tm1": (1, 5, "kiss", "b200_fixed", np.int16, 0, dict()),
+    "fixed_tm4_window": (4, 8, "kiss", "b200_fixed", np.int16, 0, dict(mode=4, modulator_extra="ofdmwindowing=20")),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have, reason="oracle/_ref binaries not built (make -C oracle binary)")
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_b200_engine_in_the_real_binary(tmp_path, case):
+    mode, n_tf, ref_engine, b200_engine, dt, P, kw = CASES[case]
+    if kw.get("poly"):
+        kw = dict(kw, polyfile=str(tmp_path / "poly.coef"))
+        write_poly_file(kw["polyfile"], [1.0, 0.05, -0.02, 0.0, 0.0], [0.0, 0.1, -0.05, 0.0, 0.0])
+    eti_path = make_eti(tmp_path, mode, n_tf)
+    ref = np.fromfile(run_binary(REF_BIN, tmp_path, "ref", eti_path, ref_engine, **kw), dt)
+    for depth in (0, 3):
+        got = np.fromfile(run_binary(B200_BIN, tmp_path, "b200_d%d" % depth, eti_path, b200_engine, depth=depth, **kw), dt)
+        assert ref.size % (n_tf - P) == 0
+        per_tf = ref.size // (n_tf - P)
+        # depth 0: every TF comes back in its own call, nothing is held back; depth D: call i returns TF i - D and
+        # the D frames in flight at the end are never flushed, like the reference's pipelined stages
+        n_got = n_tf - depth
+        assert got.size == n_got * per_tf, (got.size / per_tf, n_got)
+        n = min(n_got, n_tf - P)
+        assert n >= 2
+        a, b = got[:n * per_tf].reshape(n, per_tf), ref[:n * per_tf].reshape(n, per_tf)
+        for i in range(n):
+            if ref_engine == "kiss":
+                assert np.array_equal(a[i], b[i]), (case, depth, i)       # the fixed-point engine is bit-exact
+            elif dt is np.int16:
+                d = np.abs(a[i].astype(np.int32) - b[i].astype(np.int32))
+                assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size, (case, depth, i)
+            else:
+                assert rel_rms(a[i], b[i]) < 2e-6, (case, depth, i)
