@@ -44,6 +44,8 @@ FIR_BYTES_PER_TF = 2 * TF_SAMPLES * 8                    # 3 145 728
 # k_fir_sym reads the symbol kernel's compact layout (76 symbols x 2048 samples)
 COMPACT_SAMPLES = 76 * 2048                              # 155 648
 FIR_SYM_BYTES_PER_TF = (COMPACT_SAMPLES + TF_SAMPLES) * 8   # 2 818 048
+ETI_PER_TF_MODE = {1: 4, 2: 1, 3: 1, 4: 2}
+FP32_PEAK_TFLOPS = 72.0                                   # measured FFMA rate of this B200 pool (tools/ubench/fp32_pipes.cu)
 METRIC = "ETI frames/sec (TM I, 2.048 Msps I/Q) at 1/2/4/8 B200 vs reference CPU"
 WORKLOAD = "TM I, batched 1024 frames on 1xB200, native rate, FIRFilter enabled (default taps)"
 
@@ -108,31 +110,56 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # reference / CPU baseline
 # ---------------------------------------------------------------------------
-def cpu_chain_factory():
-    """Returns (kind, make_chain, latency) for the CPU implementation of the path."""
+def ref_kwargs(kw, tmpdir="/tmp"):
+    """Modulator(**kw) keyword set -> RefChain(**...) keyword set (the same configuration for the reference)."""
+    r = dict(mode=kw.get("mode", 1))
+    for k in ("output_rate", "normalise", "digital_gain", "gain_mode", "fixed_point", "fmt"):
+        if k in kw:
+            r[k] = kw[k]
+    if kw.get("fir_taps") is not None:
+        r["fir_taps_file"] = "default"
+    if kw.get("poly") is not None:
+        path = os.path.join(tmpdir, "bench_poly_%d.coef" % os.getpid())
+        with open(path, "w") as f:
+            f.write("1\n5\n" + "\n".join("%.9g" % c for c in kw["poly"]) + "\n")
+        r["poly_coef_file"] = path
+        r["poly_threads"] = 1
+    return r
+
+
+def cpu_chain_factory(kw=None, variant=None):
+    """Returns (kind, make_chain) for the CPU implementation of the path in configuration `kw`
+    (default: the headline workload)."""
     from oracle import refwrap
-    if refwrap.available():
+    kw = kw if kw is not None else dict(mode=MODE, fir_taps="default")
+    if refwrap.available(variant):
+        rk = ref_kwargs(kw)
+
         def mk():
-            return refwrap.RefChain(mode=MODE, fir_taps_file="default")
+            return refwrap.RefChain(variant=variant, **rk)
         return "reference", mk
+    if variant is not None:
+        raise RuntimeError("reference library variant %r not built" % variant)
     from oracle import oracle
 
     def mk2():
-        return oracle.OracleChain(mode=MODE, fir_taps=oracle.fir_default_taps())
+        return oracle.OracleChain(mode=kw.get("mode", 1), fir_taps=oracle.fir_default_taps() if kw.get("fir_taps") else None)
     return "port", mk2
 
 
-def run_cpu(n_threads, tfs_per_thread, seed=99):
+def run_cpu(n_threads, tfs_per_thread, seed=99, kw=None, variant=None):
     """n_threads independent modulators (one per host core), each fed tfs_per_thread TFs.
     Returns (eti_frames_per_s, seconds, kind)."""
-    kind, mk = cpu_chain_factory()
+    kind, mk = cpu_chain_factory(kw, variant)
+    mode = (kw or {}).get("mode", MODE)
     rng = np.random.default_rng(seed)
-    bits = rng.integers(0, 256, (8, TF_IN_BYTES), dtype=np.uint8)
+    tf_bytes = {1: 28800, 2: 7200, 3: 7296, 4: 14400}[mode]
+    bits = rng.integers(0, 256, (8, tf_bytes), dtype=np.uint8)
     chains = [mk() for _ in range(n_threads)]
     feed = (lambda c, b: c.feed_raw(b)) if kind == "reference" else (lambda c, b: c.process(b))
-    # prime the pipelined stages (reference: 2 calls of latency) outside the timed region
+    # prime the pipelined stages (reference: up to 3 calls of latency) outside the timed region
     for c in chains:
-        for i in range(3):
+        for i in range(4):
             feed(c, bits[i % 8])
     barrier = threading.Barrier(n_threads + 1)
 
@@ -153,7 +180,31 @@ def run_cpu(n_threads, tfs_per_thread, seed=99):
         t.join()
     for c in chains:
         c.close()
-    return n_threads * tfs_per_thread * ETI_PER_TF / dt, dt, kind
+    return n_threads * tfs_per_thread * ETI_PER_TF_MODE[mode] / dt, dt, kind
+
+
+def cpu_reference_for(kw, tfs_per_thread):
+    """The reference's own CPU code on this box in configuration `kw`: one modulator on one core (the reference's
+    native shape: main thread + its pipelined stages), one independent modulator per core, and the -ffast-math build
+    (BASELINE.md section 3)."""
+    from oracle import refwrap
+    if not refwrap.available():
+        return None
+    cores = host_cores()
+    out = {"cores": cores, "kind": "reference",
+           "sample": "%d TFs per modulator; FFTW replaced by the reference's vendored float KISS FFT" % tfs_per_thread}
+    try:
+        v, dt, _ = run_cpu(1, tfs_per_thread, kw=kw)
+        out["one_modulator_eti_frames_per_s"] = v
+        v, dt, _ = run_cpu(cores, tfs_per_thread, kw=kw)
+        out["all_cores_eti_frames_per_s"] = v
+        out["all_cores_seconds"] = dt
+        if refwrap.available("fast"):
+            v, dt, _ = run_cpu(cores, tfs_per_thread, kw=kw, variant="fast")
+            out["all_cores_ffast_math_eti_frames_per_s"] = v
+    except Exception as e:
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
 
 
 def host_cores():
@@ -168,7 +219,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    tfs = 24                                   # per thread per step: ~0.1-0.2 s of CPU work
+    tfs = 96                                   # per thread per step: ~0.4 s of CPU work
     for _ in range(args.warmup):
         run_cpu(cores, tfs)
     t_total, frames = 0.0, 0
@@ -203,7 +254,6 @@ RES_INFO = {
     8192000: {"out_samples": 786432, "flop": 133.7e6},
     10000000: {"out_samples": 960000, "flop": 160.6e6},
 }
-ETI_PER_TF_MODE = {1: 4, 2: 1, 3: 1, 4: 2}
 
 
 def other_configs():
@@ -224,8 +274,12 @@ def other_configs():
     ]
 
 
-def measure_config(dm, torch, name, kw, n_tf, stream, peak, steps=5, warmup=3):
-    """Device-resident throughput and per-kernel times of one configuration."""
+CPU_TFS = {"c1": 64, "c3 ": 10, "c5": 8, "c3s": 10, "c4 TM II ": 256, "c4 TM III": 256, "c4 TM IV": 128, "n4": 64}
+
+
+def measure_config(dm, torch, name, kw, n_tf, stream, peak, steps=5, warmup=3, with_cpu=False, with_e2e=True):
+    """Device-resident throughput, per-kernel times, host-delivered throughput and the reference's CPU throughput
+    of one configuration."""
     mod = dm.Modulator(max_batch=n_tf, **kw)
     g = torch.Generator(device="cpu").manual_seed(4321)
     bits = torch.randint(0, 256, (n_tf, mod.tf_in_bytes), dtype=torch.uint8, generator=g).to("cuda")
@@ -253,39 +307,152 @@ def measure_config(dm, torch, name, kw, n_tf, stream, peak, steps=5, warmup=3):
            "eti_frames_per_s": n_tf * ETI_PER_TF_MODE[mode] / (ms * 1e-3),
            "out_bytes_per_step": n_tf * mod.tf_out_bytes,
            "kernels_ms": {k: float(np.mean(v)) for k, v in kt.items()}}
+    mod.set_param("profile", 0)
+    if with_e2e:
+        # host-delivered: the same batch through dabmod_b200_process_batch, pinned host buffers both ways
+        try:
+            ob = n_tf * mod.tf_out_bytes
+            h_in = bits.cpu().pin_memory()
+            h_out = torch.empty(ob, dtype=torch.uint8).pin_memory()
+            mod.process_batch_ptr(h_in.data_ptr(), n_tf, h_out.data_ptr(), ob)
+            torch.cuda.synchronize()
+            reps = 3
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                mod.process_batch_ptr(h_in.data_ptr(), n_tf, h_out.data_ptr(), ob)
+            dt = (time.perf_counter() - t0) / reps
+            res["e2e"] = {"eti_frames_per_s": n_tf * ETI_PER_TF_MODE[mode] / dt, "ms_per_step": dt * 1e3,
+                          "d2h_GB/s": ob / dt / 1e9, "h2d_bytes_per_step": n_tf * mod.tf_in_bytes,
+                          "d2h_bytes_per_step": ob, "checksum": int(h_out[::65537].to(torch.int64).sum().item())}
+            del h_in, h_out
+        except Exception as e:
+            res["e2e"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if with_cpu:
+        key = [k for k in CPU_TFS if name.startswith(k)]
+        cpu = cpu_reference_for(kw, CPU_TFS[key[0]] if key else 16)
+        if cpu is not None:
+            res["cpu_reference"] = cpu
+            if "all_cores_eti_frames_per_s" in cpu:
+                res["speedup_vs_all_cores"] = {"device_resident": res["eti_frames_per_s"] / cpu["all_cores_eti_frames_per_s"],
+                                               "host_delivered": (res.get("e2e", {}).get("eti_frames_per_s", 0) /
+                                                                  cpu["all_cores_eti_frames_per_s"])}
     rate = kw.get("output_rate", 2048000)
     if rate in RES_INFO and mode == 1:
         k = [x for x in kt if x.startswith("k_resample")][0]
         t = float(np.mean(kt[k])) * 1e-3
         info = RES_INFO[rate]
         byt = n_tf * (TF_SAMPLES * 8 + info["out_samples"] * (mod.tf_out_bytes // mod.tf_out_samples))
+        fir_t = sum(float(np.mean(v)) for kk, v in kt.items() if kk.startswith("k_fir")) * 1e-3
+        stage_bytes = n_tf * (TF_SAMPLES * 8 + info["out_samples"] * (mod.tf_out_bytes // mod.tf_out_samples))
+        stage_flop = n_tf * (info["flop"] + 35.4e6 + 40.0 * info["out_samples"])     # resampler + FIR + poly, SURVEY 8(d)
         res["resampler"] = {"kernel": k, "ms": t * 1e3, "algorithmic_GB/s": byt / t / 1e9,
                             "frac_of_hbm_peak": byt / t / 1e9 / peak,
                             "algorithmic_TFLOP/s_fp32": n_tf * info["flop"] / t / 1e12,
+                            "frac_of_fp32_peak": n_tf * info["flop"] / t / 1e12 / FP32_PEAK_TFLOPS,
                             "note": "FP32-bound stage (17-19 flop/B > the 11 flop/B ridge): see DESIGN.md"}
+        res["fir_resample_stage"] = {"ms": (fir_t + t) * 1e3, "algorithmic_bytes": stage_bytes,
+                                     "frac_of_hbm_peak": stage_bytes / (fir_t + t) / 1e9 / peak,
+                                     "algorithmic_TFLOP/s_fp32": stage_flop / (fir_t + t) / 1e12,
+                                     "frac_of_fp32_peak": stage_flop / (fir_t + t) / 1e12 / FP32_PEAK_TFLOPS,
+                                     "fp32_peak_TFLOP/s": FP32_PEAK_TFLOPS,
+                                     "fp32_peak_source": "measured FFMA throughput, profiles/r01_ubench_fp32_pipes.txt",
+                                     "note": "north_star stage: FIRFilter + Resampler + MemlessPoly, against both roofs"}
     if kw.get("fixed_point"):
         t = float(np.mean(kt["k_symbols_fix"])) * 1e-3
         byt = n_tf * (mod.tf_in_bytes + mod.tf_out_bytes)        # bits in, int16 I/Q out
         res["symbols_fix"] = {"ms": t * 1e3, "algorithmic_GB/s": byt / t / 1e9, "frac_of_hbm_peak": byt / t / 1e9 / peak,
                               "note": "integer kernel (KISS FIXED_POINT=16 arithmetic, bit-exact), ALU/LSU bound"}
-        try:
-            from oracle import refwrap
-            if refwrap.available():
-                ref = refwrap.RefChain(mode=mode, fixed_point=True)
-                hb = bits[:16].cpu().numpy()
-                ref.feed_raw(hb[0])
-                t0 = time.perf_counter()
-                for b in hb:
-                    ref.feed_raw(b)
-                dt = time.perf_counter() - t0
-                res["cpu_reference"] = {"eti_frames_per_s": len(hb) * ETI_PER_TF_MODE[mode] / dt, "cores": 1,
-                                        "kind": "reference", "sample": "16 TFs through the reference's fixed-point chain"}
-        except Exception as e:
-            res["cpu_reference"] = {"error": str(e)}
     mod.close()
     del bits, out
     torch.cuda.empty_cache()
     return res
+
+
+def measure_binary(n_frames=4000):
+    """BASELINE configs[0]: the real program, ETI file in -> I/Q file out (TM I, native rate, complexf), through
+    InputFileReader -> EtiReader -> the reference's channel coding graph -> [chain] -> OutputFile(/dev/null):
+    oracle/_ref/odr-dabmod-ref (every source unmodified, its own threads) against oracle/_ref/odr-dabmod-b200
+    (fft_engine = b200: the same program with the chain behind BlockPartitioner on the GPU), one TF per call and with
+    the adapter's 64-TF pipeline.  In both the channel coding runs on ONE host thread (src/DabMod.cpp:593-738)."""
+    import importlib
+    import tempfile
+    eti = importlib.import_module("odr_dabmod_b200.eti")
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "odr-dabmod-ref")
+    b200_bin = os.path.join(ROOT, "oracle", "_ref", "odr-dabmod-b200")
+    if not (os.path.exists(ref_bin) and os.path.exists(b200_bin)):
+        return {"workload": "c0 binary", "error": "oracle/_ref binaries not built"}
+    tmp = tempfile.mkdtemp(prefix="dabmod_bench_")
+    path = os.path.join(tmp, "in.eti")
+    eti.synth_eti_range(1, eti.default_multiplex(), 0, n_frames, seed=8).tofile(path)
+    ini = ("[remotecontrol]\nzmqctrl=0\ntelnet=0\n[log]\nsyslog=0\n[input]\ntransport=file\nsource=%s\nloop=0\n"
+           "[modulator]\nfft_engine=%s\ngainmode=var\nmode=1\nrate=2048000\n[firfilter]\nenabled=0\n"
+           "[output]\noutput=file\n[fileoutput]\nformat=complexf\nfilename=/dev/null\n")
+    res = {"workload": "c0 TM I, ETI file input, native 2.048 Msps, no FIR/resample, file output: the real binary",
+           "eti_frames": n_frames}
+    for key, binary, engine, depth in (("reference_binary", ref_bin, "fftw", 0), ("b200_binary", b200_bin, "b200", 0),
+                                       ("b200_binary_depth64", b200_bin, "b200", 64)):
+        cfg = os.path.join(tmp, key + ".ini")
+        with open(cfg, "w") as f:
+            f.write(ini % (path, engine))
+        env = dict(os.environ, ODR_DABMOD_B200_DEPTH=str(depth))
+        try:
+            t0 = time.perf_counter()
+            r = subprocess.run([binary, cfg], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+            dt = time.perf_counter() - t0
+            res[key] = {"eti_frames_per_s": n_frames / dt, "seconds": dt, "returncode": r.returncode}
+        except Exception as e:
+            res[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+    res["note"] = ("wall clock of the whole process incl. start-up (CUDA context creation ~0.3 s for the b200 arm); "
+                   "both arms are bound by the reference's single-threaded EtiReader + channel coding "
+                   "(~0.25 ms per ETI frame), which the engine does not replace")
+    return res
+
+
+def measure_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write of one launch of `kernel` in the headline step, from an ncu capture taken
+    by this run (a child process under ncu; nothing under the profiler is timed)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:^%s" % kernel, "-s", "3", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__),
+           "--traffic-child"]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    except Exception as e:
+        return None, "%s: %s" % (type(e).__name__, e)
+    total, seen = 0.0, 0
+    import csv
+    import io
+    rows = [row for row in csv.reader(io.StringIO(r.stdout)) if len(row) > 4]
+    hdr = next((row for row in rows if "Metric Name" in row), None)
+    if hdr is None:
+        return None, "no ncu csv (%s)" % r.stdout[-200:].replace("\n", " ")
+    iname, iunit, ival = hdr.index("Metric Name"), hdr.index("Metric Unit"), hdr.index("Metric Value")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for row in rows:
+        if row is hdr or len(row) <= ival or not row[iname].startswith("dram__bytes"):
+            continue
+        total += float(row[ival].replace(",", "")) * scale.get(row[iunit], 1.0)
+        seen += 1
+    return (total, "ncu capture of this run") if seen == 2 else (None, "ncu metrics missing")
+
+
+def traffic_child():
+    """The headline step a few times, device-resident (run under ncu by measure_traffic)."""
+    import torch
+    import dabmod_loader
+    dm = dabmod_loader.load()
+    n_tf = TFS_PER_STEP
+    mod = dm.Modulator(mode=MODE, fir_taps="default", max_batch=n_tf)
+    bits = torch.randint(0, 256, (n_tf, mod.tf_in_bytes), dtype=torch.uint8).cuda()
+    out = torch.empty(n_tf * mod.tf_out_bytes, dtype=torch.uint8, device="cuda")
+    for _ in range(6):
+        mod.process_batch_device(bits.data_ptr(), n_tf, out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    mod.close()
+    return 0
 
 
 def measure_coder(dm, torch, stream, n_tf=1024, steps=5, warmup=3, with_cpu=True):
@@ -796,26 +963,32 @@ def gpu_arm(args):
         "all_kernels": {k: {"ms": kavg[k], "GB/s": bytes_per_launch[k] / (kavg[k] * 1e-3) / 1e9,
                             "frac": bytes_per_launch[k] / (kavg[k] * 1e-3) / 1e9 / peak} for k in kavg},
     }
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
-        with open(traffic_file) as f:
-            roofline["traffic"] = json.load(f).get(dom)
+    if not args.no_extras:
+        roofline["traffic"], roofline["traffic_source"] = measure_traffic(dom)
+    if roofline["traffic"] is None:
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                roofline["traffic"] = json.load(f).get(dom)
+            roofline["traffic_source"] = "profiles/traffic.json (ncu capture of an earlier run: %s)" % roofline.get("traffic_source")
 
     os.sched_setaffinity(0, all_cpus)      # the CPU legs below use every host core again
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = host_cores()
         tfs = 192
-        v, dt_cpu, kind = run_cpu(cores, tfs)
+        runs = sorted(run_cpu(cores, tfs) for _ in range(3))       # median of three ~1 s samples (48 threads on the
+        v, dt_cpu, kind = runs[1]                                   # host's cores: single samples scatter by 10-20 %)
         cpu = {"value": v, "unit": "ETI frames/s", "cores": cores, "kind": kind,
-               "sample": "%d TFs per thread x %d threads, %.1f s (same TM I + FIR default taps chain)" % (tfs, cores, dt_cpu)}
+               "sample": "median of 3 runs of %d TFs per thread x %d threads, %.1f s each (same TM I + FIR default "
+                         "taps chain); all three: %s" % (tfs, cores, dt_cpu, ", ".join("%.0f" % r[0] for r in runs))}
 
     others = None
     if world == 1 and not args.no_extras:
         others = []
         for name, kw, ntf in other_configs():
             try:
-                others.append(measure_config(dm, torch, name, kw, ntf, stream, peak))
+                others.append(measure_config(dm, torch, name, kw, ntf, stream, peak, with_cpu=not args.no_cpu))
             except Exception as e:                       # an extra must never cost the headline line
                 others.append({"workload": name, "error": str(e)})
         try:
@@ -830,6 +1003,11 @@ def gpu_arm(args):
             others.append(measure_coder(dm, torch, stream, with_cpu=not args.no_cpu))
         except Exception as e:
             others.append({"workload": "n1 coder", "error": str(e)})
+        if not args.no_cpu:
+            try:
+                others.append(measure_binary())
+            except Exception as e:
+                others.append({"workload": "c0 binary", "error": str(e)})
 
     line = {
         "metric": METRIC, "value": value, "unit": "ETI frames/s", "n_gpus": world,
@@ -881,7 +1059,10 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (other_configs key)")
     ap.add_argument("--stream-frames", type=int, default=65536,
                     help="ETI frames of the sharded-stream leg (BASELINE configs[4]); 0 skips it")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.traffic_child:
+        return traffic_child()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

@@ -205,6 +205,7 @@ struct dabmod_b200 {
     DevBuf<float> d_tii_val;
     DevBuf<float> d_window;
     DevBuf<float> d_lut;
+    DevBuf<float> d_fir_taps;      // taps of a filter longer than MAX_FIR_TAPS (k_fir_long), zero padded
     DevBuf<unsigned long long> d_clipped;
     int tii_count = 0;
 
@@ -342,6 +343,11 @@ void build_tables(dabmod_b200 *h)
     if (h->dpd_mode == DABMOD_B200_DPD_LUT) {
         std::vector<float> lut(h->dpd + 1, h->dpd + 33);
         h->d_lut.upload(lut, s);
+    }
+    if ((int)h->fir_taps.size() > MAX_FIR_TAPS) {
+        std::vector<float> t(h->fir_taps);
+        t.resize((t.size() + FIR_CHUNK - 1) / FIR_CHUNK * FIR_CHUNK, 0.0f);
+        h->d_fir_taps.upload(t, s);
     }
     if (h->fixed()) {
         // KISS plan of the mode's transform (kiss_fft.c:293-315 kf_factor, :325-355 kiss_fft_alloc)
@@ -487,6 +493,9 @@ bool fft_radices(int n, std::vector<unsigned char> &rad)
     while (n % 2 == 0) { rad.push_back(2); n /= 2; }
     for (int f : {5, 3, 7})
         while (n % f == 0) { rad.push_back((unsigned char)f); n /= f; }
+    // larger primes: a generic O(R) pass (resample.cuh generic_pass_prime); the radix is stored in a byte
+    for (int f = 11; f <= 251 && n > 1; f += 2)
+        while (n % f == 0) { rad.push_back((unsigned char)f); n /= f; }
     return n == 1 && rad.size() <= (size_t)RES_MAX_PASSES;
 }
 
@@ -624,6 +633,31 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         }
         else if (post) k_fir_sym<45, true><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
         else k_fir_sym<45, false><<<fgrid, FIRS_THREADS, 0, s>>>(fp);
+        CUDA_CHECK(cudaGetLastError());
+        prof_fir.end();
+        launches++;
+    }
+    else if (fir && (int)h->fir_taps.size() > MAX_FIR_TAPS) {
+        // any tap count (FIRFilter.cpp:95-141): taps in a device table, window in dynamic shared memory
+        FirLongParams fp{};
+        fp.in = reinterpret_cast<const float2 *>(sp.out);
+        fp.out = dst;
+        fp.tf_samples = m.tf_samples;
+        fp.tiles_per_tf = (m.tf_samples + FIR_TILE - 1) / FIR_TILE;
+        fp.ntaps = (int)h->fir_taps.size();
+        fp.taps = h->d_fir_taps.p;
+        fp.post = make_post(h, post);
+        const size_t smem = fir_long_smem(fp.ntaps);
+        const int fgrid = (int)(n_tf * fp.tiles_per_tf);
+        ProfScope prof_fir(h, "k_fir_long", s);
+        if (post) {
+            CUDA_CHECK(cudaFuncSetAttribute(k_fir_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fir_long<true><<<fgrid, FIR_THREADS, smem, s>>>(fp);
+        }
+        else {
+            CUDA_CHECK(cudaFuncSetAttribute(k_fir_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fir_long<false><<<fgrid, FIR_THREADS, smem, s>>>(fp);
+        }
         CUDA_CHECK(cudaGetLastError());
         prof_fir.end();
         launches++;
@@ -845,8 +879,8 @@ void validate_config(const dabmod_b200_config &c)
     if (c.mode < 0 || c.mode > 4) throw ApiError(DABMOD_B200_EINVAL, "DabModulator::setMode invalid mode size");
     if (c.gain_mode < 0 || c.gain_mode > 2) throw ApiError(DABMOD_B200_EINVAL, "Internal error: invalid gainmode");
     if (c.fir_ntaps < 0 || (c.fir_ntaps > 0 && !c.fir_taps)) throw ApiError(DABMOD_B200_EINVAL, "FIRFilter: taps missing");
-    if (c.fir_ntaps > MAX_FIR_TAPS)
-        throw ApiError(DABMOD_B200_EUNSUPPORTED, "FIRFilter: more than 128 taps are not supported");
+    if (c.fir_ntaps > MAX_FIR_TAPS_LONG)
+        throw ApiError(DABMOD_B200_EUNSUPPORTED, "FIRFilter: more than " + std::to_string(MAX_FIR_TAPS_LONG) + " taps are not supported");
     if (c.dpd_mode < 0 || c.dpd_mode > 2 || (c.dpd_mode && !c.dpd_coefs))
         throw ApiError(DABMOD_B200_EINVAL, "MemlessPoly: invalid coefficients");
     format_bytes(c.format);
@@ -990,7 +1024,7 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
                                    " do not tile the transmission frame (the reference reads out of bounds here)");
             if (!fft_radices(rp.ni, h->rad_in) || !fft_radices(rp.no, h->rad_out))
                 throw ApiError(DABMOD_B200_EUNSUPPORTED,
-                               "Resampler: FFT size " + std::to_string(rp.no) + " has a prime factor above 7");
+                               "Resampler: FFT size " + std::to_string(rp.no) + " has a prime factor above 251");
             h->rp = rp;
             h->has_res = true;
             h->res_up = rp.ni == RU_NI && rp.M == 1 && rp.L >= 2 && rp.L <= (uint64_t)RU_MAX_L;
@@ -1453,11 +1487,13 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             else if (n == "taps") {
                 int cnt; ss >> cnt;
                 if (cnt <= 0) throw ApiError(DABMOD_B200_EINVAL, "FIRFilter: taps file has invalid format.");
-                if (cnt > MAX_FIR_TAPS) throw ApiError(DABMOD_B200_EUNSUPPORTED, "FIRFilter: more than 128 taps");
+                if (cnt > MAX_FIR_TAPS_LONG)
+                    throw ApiError(DABMOD_B200_EUNSUPPORTED, "FIRFilter: more than " + std::to_string(MAX_FIR_TAPS_LONG) + " taps");
                 if (!h->has_fir()) throw ApiError(DABMOD_B200_ESTATE, "FIRFilter is not part of this chain");
                 std::vector<float> t(cnt);
                 for (auto &x : t) ss >> x;
                 h->fir_taps = t;
+                h->tables_dirty = true;        // taps above MAX_FIR_TAPS live in a device table
             }
             else if (n == "coefs") {
                 if (h->dpd_mode == 0) throw ApiError(DABMOD_B200_ESTATE, "MemlessPoly is not part of this chain");

@@ -982,6 +982,98 @@ __global__ void __launch_bounds__(FIR_THREADS) k_fir(const __grid_constant__ Fir
 }
 
 // ---------------------------------------------------------------------------
+// k_fir_long: tap counts above MAX_FIR_TAPS (FIRFilter::load_filter_taps takes any count,
+// src/FIRFilter.cpp:95-141).  Same tile, same ascending tap order and the same packed multiply-adds as
+// k_fir<0>; the taps come from global memory (uniform loads, a chunk of 16 at a time) and the input window
+// of FIR_TILE + ntaps samples lives in dynamic shared memory.
+// ---------------------------------------------------------------------------
+constexpr int MAX_FIR_TAPS_LONG = 16384;
+
+struct FirLongParams {
+    const float2 *in;
+    void *out;
+    int tf_samples;
+    int tiles_per_tf;
+    int ntaps;
+    const float *taps;    // ntaps floats, zero padded to a multiple of FIR_CHUNK (device)
+    PostParams post;
+};
+
+inline size_t fir_long_smem(int ntaps)
+{
+    const int span = FIR_TILE + ((ntaps + FIR_CHUNK - 1) / FIR_CHUNK) * FIR_CHUNK;
+    return sizeof(float2) * (size_t)(span + span / 16 + 8);
+}
+
+template <bool POST>
+__global__ void __launch_bounds__(FIR_THREADS) k_fir_long(const __grid_constant__ FirLongParams p)
+{
+    extern __shared__ __align__(16) unsigned char fir_long_raw[];
+    float2 *xs = reinterpret_cast<float2 *>(fir_long_raw);
+    const int tid = threadIdx.x;
+    const int tf = blockIdx.x / p.tiles_per_tf;
+    const int tile = blockIdx.x - tf * p.tiles_per_tf;
+    const int n0 = tile * FIR_TILE;
+    const float2 *in = p.in + (size_t)tf * p.tf_samples;
+    const int span = FIR_TILE + ((p.ntaps + FIR_CHUNK - 1) / FIR_CHUNK) * FIR_CHUNK;
+
+    for (int i = 2 * tid; i < span; i += 2 * FIR_THREADS) {
+        const int n = n0 + i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n + 1 < p.tf_samples) v = __ldg(reinterpret_cast<const float4 *>(in + n));
+        else if (n < p.tf_samples) {
+            const float2 a = __ldg(in + n);
+            v.x = a.x; v.y = a.y;
+        }
+        xs[fpad(i)] = make_float2(v.x, v.y);
+        xs[fpad(i + 1)] = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+
+    float2 acc[FIR_M];
+#pragma unroll
+    for (int m = 0; m < FIR_M; m++) acc[m] = make_float2(0.f, 0.f);
+    for (int c = 0; c * FIR_CHUNK < p.ntaps; c++) {
+        float tp[FIR_CHUNK];
+#pragma unroll
+        for (int j = 0; j < FIR_CHUNK; j++) tp[j] = __ldg(p.taps + c * FIR_CHUNK + j);
+        const int i0 = tid * FIR_M + c * FIR_CHUNK;
+#pragma unroll
+        for (int i = 0; i < FIR_M + FIR_CHUNK - 1; i++) {
+            const float2 v = xs[fpad(i0 + i)];
+#pragma unroll
+            for (int m = 0; m < FIR_M; m++) {
+                const int j = i - m;
+                if (j >= 0 && j < FIR_CHUNK) acc[m] = __ffma2_rn(v, make_float2(tp[j], tp[j]), acc[m]);
+            }
+        }
+    }
+    __syncthreads();
+    float4 *ys = reinterpret_cast<float4 *>(xs);
+#pragma unroll
+    for (int m = 0; m < FIR_M; m += 2)
+        ys[tid * (FIR_M / 2 + 1) + m / 2] = make_float4(acc[m].x, acc[m].y, acc[m + 1].x, acc[m + 1].y);
+    __syncthreads();
+
+    unsigned clip = 0;
+    const size_t obase = (size_t)tf * p.tf_samples + n0;
+#pragma unroll
+    for (int k = 0; k < FIR_M / 2; k++) {
+        const int q = k * FIR_THREADS + tid;
+        const int n = 2 * q;
+        const float4 v = ys[q + (q >> 3)];
+        if (!POST && n0 + n + 1 < p.tf_samples) {
+            reinterpret_cast<float4 *>(reinterpret_cast<float2 *>(p.out) + obase)[q] = v;
+        }
+        else {
+            if (n0 + n < p.tf_samples) store_sample<POST>(p.out, obase + n, make_float2(v.x, v.y), p.post, clip);
+            if (n0 + n + 1 < p.tf_samples) store_sample<POST>(p.out, obase + n + 1, make_float2(v.z, v.w), p.post, clip);
+        }
+    }
+    if (POST && p.post.format != 0) flush_clip(p.post, clip);
+}
+
+// ---------------------------------------------------------------------------
 // k_fir_sym: the same filter for TM I fed by k_symbols_w in its compact layout
 // ([tf][symbol 1..L][N] samples, no null symbol, no cyclic prefix).  One CTA = one
 // OFDM symbol.  Two facts about the guard-interval stream make this cheaper than

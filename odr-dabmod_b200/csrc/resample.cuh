@@ -163,6 +163,29 @@ __device__ __forceinline__ void generic_pass(const float2 *src, float2 *dst, int
     }
 }
 
+// A pass of any prime radix R (11, 13, ...: output rates whose L carries such a factor, e.g. 2.816 Msps = 11/8):
+// one output per loop iteration, O(R) terms each, the inter-pass twiddle and the R-th root of unity folded into
+// one look-up in the N-entry root table.  Completeness, not speed.
+template <bool INV>
+__device__ __forceinline__ void generic_pass_prime(const float2 *src, float2 *dst, int N, int Ns, int R, const float2 *tw,
+                                                   int tid, int nth)
+{
+    const int nb = N / R, step = N / (Ns * R), rstep = N / R;
+    for (int idx = tid; idx < N; idx += nth) {
+        const int m = idx / nb, b = idx - m * nb;
+        const int k = b % Ns;
+        const long long e1 = (long long)k * step + (long long)m * rstep;   // exponent per unit of r
+        float ax = 0.f, ay = 0.f;
+        for (int r = 0; r < R; r++) {
+            const float2 x = src[b + r * nb];
+            const float2 w = tw_dir<INV>(__ldg(tw + (int)((e1 * r) % N)));
+            ax = fmaf(x.x, w.x, fmaf(-x.y, w.y, ax));
+            ay = fmaf(x.x, w.y, fmaf(x.y, w.x, ay));
+        }
+        dst[(b - k) * R + k + m * Ns] = make_float2(ax, ay);
+    }
+}
+
 template <bool INV>
 __device__ __forceinline__ void generic_fft(float2 *&src, float2 *&dst, int N, const unsigned char *rad, int n_rad,
                                             const float2 *tw, int tid, int nth)
@@ -177,7 +200,8 @@ __device__ __forceinline__ void generic_fft(float2 *&src, float2 *&dst, int N, c
             case 2: generic_pass<2, INV>(src, dst, N, Ns, tw, tid, nth); break;
             case 3: generic_pass<3, INV>(src, dst, N, Ns, tw, tid, nth); break;
             case 5: generic_pass<5, INV>(src, dst, N, Ns, tw, tid, nth); break;
-            default: generic_pass<7, INV>(src, dst, N, Ns, tw, tid, nth); break;
+            case 7: generic_pass<7, INV>(src, dst, N, Ns, tw, tid, nth); break;
+            default: generic_pass_prime<INV>(src, dst, N, Ns, R, tw, tid, nth); break;
         }
         Ns *= R;
         __syncthreads();
@@ -186,7 +210,7 @@ __device__ __forceinline__ void generic_fft(float2 *&src, float2 *&dst, int N, c
 }
 
 // ---------------------------------------------------------------------------
-// k_resample_generic: any Ni / No whose prime factors are in {2, 3, 5, 7}.
+// k_resample_generic: any Ni / No whose prime factors are at most 251 (2, 3, 5, 7 as register butterflies).
 // Persistent CTAs stride over the hops; two ping-pong buffers of max(Ni, No)
 // points live in shared memory when they fit, else in a per-CTA slice of
 // `scratch` (L2-resident).  This is the completeness path; the TM I hot

@@ -13,6 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(HERE, "_ref", "libdabmod_ref.so")
+REF_LIB_FAST = os.path.join(HERE, "_ref", "fast", "libdabmod_ref.so")     # the same sources with -ffast-math
 
 TF_BYTES = {1: 75 * 384, 2: 75 * 96, 3: 152 * 48, 4: 75 * 192}
 TF_SAMPLES = {1: 196608, 2: 49152, 3: 49152, 4: 98304}
@@ -44,17 +45,32 @@ class _RefCfg(ctypes.Structure):
     ]
 
 
-def available():
-    return os.path.exists(REF_LIB)
+def available(variant=None):
+    return os.path.exists(REF_LIB_FAST if variant == "fast" else REF_LIB)
 
 
 _lib = None
+_libs = {}
 
 
-def lib():
+def lib(variant=None):
     global _lib
+    if variant == "fast":
+        if "fast" not in _libs:
+            saved, _lib = _lib, None
+            try:
+                _libs["fast"] = _load(REF_LIB_FAST)
+            finally:
+                _lib = saved
+        return _libs["fast"]
     if _lib is None:
-        _lib = ctypes.CDLL(REF_LIB)
+        _lib = _load(REF_LIB)
+    return _lib
+
+
+def _load(path):
+    if True:
+        _lib = ctypes.CDLL(path)
         _lib.ref_create.restype = ctypes.c_void_p
         _lib.ref_create.argtypes = [ctypes.POINTER(_RefCfg)]
         _lib.ref_latency.restype = ctypes.c_int
@@ -77,7 +93,8 @@ class RefChain:
     def __init__(self, mode=1, gain_mode="var", output_rate=2048000, clock_rate=0,
                  digital_gain=1.0, normalise=1.0, gain_variance=4.0, window_overlap=0,
                  cfr=None, tii=None, fir_taps_file=None, poly_coef_file=None,
-                 poly_threads=1, fmt=None, stop_after=None, fixed_point=False):
+                 poly_threads=1, fmt=None, stop_after=None, fixed_point=False, variant=None):
+        self._lib = lib(variant)
         c = _RefCfg()
         c.mode = mode
         c.gain_mode = GAIN_MODES[gain_mode]
@@ -104,27 +121,27 @@ class RefChain:
         c.fixed_point = 1 if fixed_point else 0
         self._cfg = c
         self.mode = mode
-        self._h = lib().ref_create(ctypes.byref(c))
+        self._h = self._lib.ref_create(ctypes.byref(c))
         if not self._h:
-            raise RuntimeError("ref_create: " + lib().ref_last_error().decode())
-        self.latency = lib().ref_latency(self._h)
+            raise RuntimeError("ref_create: " + self._lib.ref_last_error().decode())
+        self.latency = self._lib.ref_latency(self._h)
         self._out = np.empty(64 << 20, np.uint8)
 
     def feed(self, bits):
         """Feed one TF; returns raw output bytes (np.uint8, possibly empty)."""
         bits = np.ascontiguousarray(bits, np.uint8)
-        n = lib().ref_process(self._h, bits.ctypes.data, bits.size,
+        n = self._lib.ref_process(self._h, bits.ctypes.data, bits.size,
                               self._out.ctypes.data, self._out.size)
         if n < 0:
-            raise RuntimeError("ref_process: " + lib().ref_last_error().decode())
+            raise RuntimeError("ref_process: " + self._lib.ref_last_error().decode())
         return self._out[:n].copy()
 
     def feed_raw(self, bits):
         """Like feed() but leaves the result in the internal buffer (timing loops)."""
-        n = lib().ref_process(self._h, bits.ctypes.data, bits.size,
+        n = self._lib.ref_process(self._h, bits.ctypes.data, bits.size,
                               self._out.ctypes.data, self._out.size)
         if n < 0:
-            raise RuntimeError("ref_process: " + lib().ref_last_error().decode())
+            raise RuntimeError("ref_process: " + self._lib.ref_last_error().decode())
         return n
 
     def run(self, bits_tfs, dtype=np.complex64):
@@ -144,13 +161,13 @@ class RefChain:
     def get_param(self, name):
         """OfdmGeneratorCF32::get_parameter of this chain ("clip_stats", "papr", ...)."""
         buf = ctypes.create_string_buffer(512)
-        if lib().ref_ofdm_get_parameter(self._h, name.encode(), buf, 512) != 0:
-            raise RuntimeError(lib().ref_last_error().decode())
+        if self._lib.ref_ofdm_get_parameter(self._h, name.encode(), buf, 512) != 0:
+            raise RuntimeError(self._lib.ref_last_error().decode())
         return buf.value.decode()
 
     def close(self):
         if self._h:
-            lib().ref_destroy(self._h)
+            self._lib.ref_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -116,6 +116,38 @@ def test_fir_tap_counts(dm, rng, ntaps):
     assert rel_rms(out[0], ora[0]) < TOL
 
 
+@pytest.mark.parametrize("mode,ntaps,fmt", [(2, 129, None), (2, 300, None), (4, 1000, "s16"), (1, 2049, None)])
+def test_fir_long_filters(dm, rng, mode, ntaps, fmt):
+    """FIRFilter::load_filter_taps takes any tap count (src/FIRFilter.cpp:95-141): above 128 taps the filter runs
+    from a device tap table (k_fir_long), also longer than a whole symbol; the window still ends in zeros at the TF end,
+    and the RC `taps` parameter switches between the short and the long kernel."""
+    bits = bits_for(rng, mode, 2)
+    taps = (rng.standard_normal(ntaps) / np.sqrt(ntaps)).astype(np.float32)
+    kw = dict(fmt=fmt, digital_gain=0.5) if fmt else {}
+    ora = oracle.OracleChain(mode=mode, fir_taps=taps, **kw).run(bits)
+    mod = dm.Modulator(mode=mode, fir_taps=taps, max_batch=2, **kw)
+    mod.set_param("profile", 1)
+    out = mod.process_batch(bits)
+    assert "k_fir_long" in [k for k, _ in mod.kernel_times()]
+    for i in range(2):
+        if fmt:
+            d = np.abs(out[i].astype(np.int32) - ora[i].astype(np.int32))
+            assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size
+        else:
+            assert rel_rms(out[i], ora[i]) < TOL, i
+    if not fmt:
+        short = (rng.standard_normal(20) / 4).astype(np.float32)
+        mod.set_param("taps", "20 " + " ".join("%.9g" % t for t in short))
+        mod.reset()
+        a = mod.process_batch(bits)
+        assert "k_fir" in [k for k, _ in mod.kernel_times()] and "k_fir_long" not in [k for k, _ in mod.kernel_times()]
+        want = oracle.OracleChain(mode=mode, fir_taps=short).run(bits)
+        assert rel_rms(a[0], want[0]) < TOL
+        mod.set_param("taps", "%d " % ntaps + " ".join("%.9g" % t for t in taps))
+        mod.reset()
+        assert np.array_equal(mod.process_batch(bits).view(np.uint32), out.view(np.uint32))
+
+
 def test_input_edge_patterns(dm):
     """All-zero, all-one and alternating bit blocks (every bit pattern is valid QPSK input)."""
     m = oracle.mode_params(1)
@@ -145,7 +177,10 @@ def test_errors(dm, rng):
 # Resampler (Resampler.cpp:131-195): FFT overlap-add with state across TFs
 # ---------------------------------------------------------------------------
 RES_CASES = [(1, 8192000), (1, 10000000), (2, 4096000), (1, 1536000), (4, 2500000), (3, 2400000), (2, 3200000),
-             (1, 4000000), (1, 6000000), (1, 8000000)]
+             (1, 4000000), (1, 6000000), (1, 8000000),
+             # output transform sizes with a prime factor above 7 (generic O(R) pass): 5632 = 2^9 * 11, 1664 = 2^7 * 13,
+             # and down-sampling to 2^7 * 11 / 2^8 * 23
+             (1, 2816000), (2, 3328000), (2, 1408000), (4, 1472000)]
 
 
 @pytest.mark.parametrize("mode,rate", RES_CASES)
