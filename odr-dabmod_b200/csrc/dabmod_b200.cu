@@ -25,6 +25,7 @@
 #include "resample_q.cuh"
 #include "symbols_fixed.cuh"
 #include "symbols_warp.cuh"
+#include "symbols_warp_g.cuh"
 #include "tables.h"
 
 using namespace dabmod;
@@ -206,6 +207,8 @@ struct dabmod_b200 {
     DevBuf<float> d_window;
     DevBuf<float> d_lut;
     DevBuf<float> d_fir_taps;      // taps of a filter longer than MAX_FIR_TAPS (k_fir_long), zero padded
+    DevBuf<float2> d_tii_frame;    // one frame through k_symbols: its null symbol is the stream's TII symbol (k_tii_fill)
+    DevBuf<uint8_t> d_tii_bits;    // that frame's (all-zero) input block
     DevBuf<unsigned long long> d_clipped;
     int tii_count = 0;
 
@@ -234,6 +237,7 @@ struct dabmod_b200 {
     bool res_q = false;            // k_resample_q applies (Ni = 4096, No = P * 4000, P = 2..5)
     bool allow_res_up = true;      // "res_kernel" knob: 0 = always the generic kernel
     int res_kernel = 1;            //   2 = the older variant of a fast kernel where two exist
+    bool fuse_proto = false;       // "fuse_proto": timing prototype of the fused symbol + FIR kernel (wrong seams)
     int res_dbg = 0;               // "res_dbg": profiling aid, skips parts of the resampler kernels (wrong results)
     size_t res_smem = 0;
 
@@ -570,10 +574,15 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     sp.post = make_post(h, sym_post);
 
     const bool sym_opt = c.cfr_enable != 0 || c.window_overlap > 0;
-    const bool warp_kernel = m.N == SW_N && h->use_warp_kernel && !sym_opt && !h->use_cic && h->tii_count == 0;
+    // TII frames (every second one) differ from plain frames in the null symbol only, and that symbol is one
+    // constant vector per stream (k_tii_fill): with enough frames in the call the warp-per-symbol kernels run and
+    // the TII symbols are filled in afterwards; the general kernel handles CicEq and short calls
+    const bool tii_fill = h->tii_count > 0 && !h->use_cic && n_tf >= 16;
+    const bool warp_ok = h->use_warp_kernel && !sym_opt && !h->use_cic && (h->tii_count == 0 || tii_fill);
+    const bool warp_kernel = m.N == SW_N && warp_ok;
     // ... followed by the default-length FIR: the symbol kernel leaves out null symbol and cyclic prefix,
-    // k_fir_sym works symbol by symbol on that compact layout (kernels.cuh)
-    const bool compact = warp_kernel && fir && h->fir_taps.size() == 45 && h->use_fir_sym;
+    // k_fir_sym works symbol by symbol on that compact layout (kernels.cuh); not with TII (the null symbol is not zero)
+    const bool compact = warp_kernel && fir && h->fir_taps.size() == 45 && h->use_fir_sym && h->tii_count == 0;
     // TM I without the optional per-carrier features: one warp per symbol (symbols_warp.cuh)
     if (warp_kernel) {
         SymWParams wp{};
@@ -584,7 +593,19 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         // persistent: one CTA per SM, every warp takes one contiguous range of the batch's symbols
         const long long n_sym = (long long)n_tf * m.L;
         const int wgrid = (int)std::min<long long>((n_sym + SW_WARPS - 1) / SW_WARPS, h->sm_count);
-        ProfScope prof_w(h, "k_symbols_w", s);
+        ProfScope prof_w(h, h->fuse_proto ? "k_symbols_w_fuse" : "k_symbols_w", s);
+        if (h->fuse_proto && !sym_post) {
+            for (size_t j = 0; j < 45 && j < h->fir_taps.size(); j++) wp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
+            wp.compact = 0;
+            wp.s.out = dst;
+            auto kern = k_symbols_w<false, true>;
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymWSmem)));
+            kern<<<wgrid, SW_THREADS, sizeof(SymWSmem), s>>>(wp);
+            CUDA_CHECK(cudaGetLastError());
+            prof_w.end();
+            launches++;
+            return;
+        }
         if (sym_post) {
             CUDA_CHECK(cudaFuncSetAttribute(k_symbols_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)sizeof(SymWSmem)));
@@ -594,6 +615,31 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
             CUDA_CHECK(cudaFuncSetAttribute(k_symbols_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)sizeof(SymWSmem)));
             k_symbols_w<false><<<wgrid, SW_THREADS, sizeof(SymWSmem), s>>>(wp);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        prof_w.end();
+        launches++;
+    }
+    else if ((m.N == 1024 || m.N == 512) && warp_ok) {
+        // TM IV / II without the optional per-carrier features: 64 / R1 symbols per warp (symbols_warp_g.cuh)
+        SymWgParams wp{};
+        wp.s = sp;
+        wp.twiddle = reinterpret_cast<const float2 *>(h->d_twiddle_w.p);
+        wp.n_tf = (int)n_tf;
+        const int G = 2048 / m.N;
+        wp.n_groups = (m.L + G - 1) / G;
+        const long long n_grp = (long long)n_tf * wp.n_groups;
+        const int wgrid = (int)std::min<long long>((n_grp + SW_WARPS - 1) / SW_WARPS, h->sm_count);
+        ProfScope prof_w(h, "k_symbols_wg", s);
+        auto go = [&](auto kern, size_t smem) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<wgrid, SW_THREADS, smem, s>>>(wp);
+        };
+        switch (m.N * 2 + (sym_post ? 1 : 0)) {
+            case 2048: go(k_symbols_wg<32, false>, sizeof(SymWgSmem<32>)); break;
+            case 2049: go(k_symbols_wg<32, true>, sizeof(SymWgSmem<32>)); break;
+            case 1024: go(k_symbols_wg<16, false>, sizeof(SymWgSmem<16>)); break;
+            default: go(k_symbols_wg<16, true>, sizeof(SymWgSmem<16>)); break;
         }
         CUDA_CHECK(cudaGetLastError());
         prof_w.end();
@@ -611,6 +657,38 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     CUDA_CHECK(cudaGetLastError());
     prof_sym.end();
     launches++;
+    }
+
+    if (tii_fill && (warp_kernel || ((m.N == 1024 || m.N == 512) && warp_ok))) {
+        // one frame through the general kernel (its null symbol is the TII symbol), then into every TII frame
+        if (!h->d_tii_frame.p) {
+            h->d_tii_frame.alloc((size_t)m.tf_samples);
+            h->d_tii_bits.alloc((size_t)m.tf_in_bytes);
+            CUDA_CHECK(cudaMemsetAsync(h->d_tii_bits.p, 0, (size_t)m.tf_in_bytes, s));
+        }
+        SymParams tp = sp;
+        tp.bits = h->d_tii_bits.p;
+        tp.out = h->d_tii_frame.p;
+        tp.tf_offset = 0;                               // frame 0 of a stream carries the TII symbol
+        tp.post = PostParams{};
+        tp.groups_per_chunk = 2;                        // the null symbol and symbol 1 are all that is needed
+        tp.n_chunks = 1;
+        ProfScope prof_t(h, "k_symbols", s);
+        switch (m.N) {
+            case 2048: launch_symbols_n<2048>(tp, false, false, 1, s); break;
+            case 1024: launch_symbols_n<1024>(tp, false, false, 1, s); break;
+            default: launch_symbols_n<512>(tp, false, false, 1, s); break;
+        }
+        CUDA_CHECK(cudaGetLastError());
+        prof_t.end();
+        launches++;
+        const int fgrid = (int)std::min<size_t>(n_tf * (size_t)((m.null_size + 255) / 256), (size_t)h->sm_count * 8);
+        ProfScope prof_f(h, "k_tii_fill", s);
+        if (sym_post) k_tii_fill<true><<<fgrid, 256, 0, s>>>(h->d_tii_frame.p, sp.out, m.null_size, m.tf_samples, (int)n_tf, stream_tf, sp.post);
+        else k_tii_fill<false><<<fgrid, 256, 0, s>>>(h->d_tii_frame.p, sp.out, m.null_size, m.tf_samples, (int)n_tf, stream_tf, sp.post);
+        CUDA_CHECK(cudaGetLastError());
+        prof_f.end();
+        launches++;
     }
 
     if (fir && compact) {
@@ -1006,6 +1084,17 @@ int dabmod_b200_create(const dabmod_b200_config *cfg, dabmod_b200 **out)
                     tww.push_back((float)cos(a));
                     tww.push_back((float)sin(a));
                 }
+            h->d_twiddle_w.upload(tww, h->s_compute);
+            CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+        }
+        else {
+            // k_symbols_wg (TM II / III / IV): the N roots of unity, its second-pass table is built from them
+            std::vector<float> tww;
+            for (int k = 0; k < h->m.N; k++) {
+                const double a = 2.0 * M_PI * (double)k / (double)h->m.N;
+                tww.push_back((float)cos(a));
+                tww.push_back((float)sin(a));
+            }
             h->d_twiddle_w.upload(tww, h->s_compute);
             CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
         }
@@ -1452,6 +1541,7 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             else if (n == "fir_kernel") { int v; ss >> v; h->use_fir_sym = v != 0; h->fir_kernel = v; }
             else if (n == "res_kernel") { int v; ss >> v; h->allow_res_up = v != 0; h->res_kernel = v; }
             else if (n == "res_dbg") { int v; ss >> v; h->res_dbg = v; }
+            else if (n == "fuse_proto") { int v; ss >> v; h->fuse_proto = v != 0; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {
                 std::string v; ss >> v;

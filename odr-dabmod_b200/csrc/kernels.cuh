@@ -982,6 +982,28 @@ __global__ void __launch_bounds__(FIR_THREADS) k_fir(const __grid_constant__ Fir
 }
 
 // ---------------------------------------------------------------------------
+// k_tii_fill: the TII null symbol for the warp-per-symbol kernels.  The TII symbol (TII.cpp:213-245) carries the
+// phase reference on a fixed set of carriers and borrows the gain of symbol 1 (GainControl.cpp:139-144), which is
+// the phase reference symbol itself: neither depends on the frame's bits, so the null symbol of every TII frame of
+// a stream is ONE constant vector of null_size samples.  It is produced once per call by the general kernel
+// (k_symbols on a single frame) and this kernel copies it into every frame where the TII toggles on
+// (TII.cpp:225-242: every second frame), through the configured epilogue.
+// ---------------------------------------------------------------------------
+template <bool POST>
+__global__ void __launch_bounds__(256) k_tii_fill(const float2 *null_sym, void *out, int null_size, int tf_samples, int n_tf,
+                                                  unsigned long long tf_offset, PostParams post)
+{
+    unsigned clip = 0;
+    const int per_tf = (null_size + 255) / 256;
+    for (long long b = blockIdx.x; b < (long long)n_tf * per_tf; b += gridDim.x) {
+        const int tf = (int)(b / per_tf), i = (int)(b - (long long)tf * per_tf) * 256 + threadIdx.x;
+        if (((tf_offset + tf) & 1) != 0 || i >= null_size) continue;
+        store_sample<POST>(out, (size_t)tf * tf_samples + i, __ldg(null_sym + i), post, clip);
+    }
+    if (POST && post.format != 0) flush_clip(post, clip);
+}
+
+// ---------------------------------------------------------------------------
 // k_fir_long: tap counts above MAX_FIR_TAPS (FIRFilter::load_filter_taps takes any count,
 // src/FIRFilter.cpp:95-141).  Same tile, same ascending tap order and the same packed multiply-adds as
 // k_fir<0>; the taps come from global memory (uniform loads, a chunk of 16 at a time) and the input window

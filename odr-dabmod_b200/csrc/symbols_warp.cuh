@@ -53,6 +53,7 @@ struct SymWParams {
     SymParams s;                            // shared with k_symbols
     const float2 *twiddle_w;                // 31 * 64 entries
     int n_tf;
+    float2 taps[45];                        // FUSE: the default FIR taps as (tap, tap) pairs
     int compact;                            // 1: write only the N samples of every data symbol, back to back
                                             // ([tf][s-1][N], no null symbol, no cyclic prefix): the layout
                                             // k_fir_sym reads (it rebuilds the guard interval itself)
@@ -110,7 +111,7 @@ __device__ __forceinline__ void sw_bulk_store(void *gdst, const void *ssrc, int 
                  : "memory");
 }
 
-template <bool POST>
+template <bool POST, bool FUSE = false>
 __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_constant__ SymWParams pw)
 {
     const SymParams &p = pw.s;
@@ -375,10 +376,63 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                     // nobody waits for the memory system.
 #pragma unroll
                     for (int i = 0; i < 64; i++) xb[lane + 32 * i] = cscale(y[i], g_sym);
+                    if (FUSE) {
+                        // PROTOTYPE (timing only, seams not wired): the 45-tap filter in place over the staged symbol,
+                        // a lane owning 17 consecutive outputs per pass (odd lane stride: conflict free)
+                        __syncwarp();
+#pragma unroll 1
+                        for (int pass = 0; pass < 4; pass++) {
+                            const int k0 = 17 * (32 * pass + lane);
+                            float2 acc[17];
+#pragma unroll
+                            for (int m = 0; m < 17; m++) acc[m] = make_float2(0.f, 0.f);
+                            const bool on = k0 + 16 < 2004;
+                            if (on) {
+                                const float2 *x = xb + k0;
+#pragma unroll
+                                for (int i = 0; i < 17 + 45 - 1; i++) {
+                                    const float2 v = x[i];
+#pragma unroll
+                                    for (int m = 0; m < 17; m++) {
+                                        const int j = i - m;
+                                        if (j >= 0 && j < 45) acc[m] = __ffma2_rn(v, pw.taps[j], acc[m]);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            if (on) {
+#pragma unroll
+                                for (int m = 0; m < 17; m++) xb[k0 + m] = acc[m];
+                            }
+                        }
+                        {
+                            // the two 44-output seams: 3 outputs per lane
+                            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+                            const float2 *x = xb + 3 * lane;
+#pragma unroll
+                            for (int i = 0; i < 47; i++) {
+                                const float2 v = x[i + 1900 - 3 * 16];
+                                if (i < 45) a0 = __ffma2_rn(v, pw.taps[i], a0);
+                                if (i >= 1 && i < 46) a1 = __ffma2_rn(v, pw.taps[i - 1], a1);
+                                if (i >= 2) a2 = __ffma2_rn(v, pw.taps[i - 2], a2);
+                            }
+                            __syncwarp();
+                            sm.code[warp][0] = 0;
+                            float2 *sb = reinterpret_cast<float2 *>(sm.code[warp]);
+                            sb[3 * lane] = a0; sb[3 * lane + 1] = a1; sb[3 * lane + 2] = a2;
+                        }
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        if (pw.compact) {
+                        if (FUSE) {
+                            float2 *gout = reinterpret_cast<float2 *>(p.out) + pos;
+                            sw_bulk_store(gout + pre, xb, 2004 * (int)sizeof(float2));
+                            sw_bulk_store(gout + 44, xb + 1544, 460 * (int)sizeof(float2));
+                            sw_bulk_store(gout, reinterpret_cast<float2 *>(sm.code[warp]), 44 * (int)sizeof(float2));
+                            sw_bulk_store(gout + pre + 2004, reinterpret_cast<float2 *>(sm.code[warp]) + 44, 44 * (int)sizeof(float2));
+                        }
+                        else if (pw.compact) {
                             float2 *gout = reinterpret_cast<float2 *>(p.out) + ((size_t)tf * L + (s - 1)) * N;
                             sw_bulk_store(gout, xb, N * (int)sizeof(float2));
                         }

@@ -332,6 +332,51 @@ def test_tii_modes_without_tii(dm, rng):
     assert rel_rms(out[0], ora[0]) < TOL
 
 
+@pytest.mark.parametrize("kw", [dict(mode=1, tii=(1, 11, 0), fir_taps="default"), dict(mode=1, tii=(7, 33, 1)),
+                                dict(mode=2, tii=(3, 20, 0), fmt="s16", digital_gain=0.8), dict(mode=2, tii=(2, 5, 0), gain_mode="max")],
+                         ids=["tm1_fir", "tm1_old_variant", "tm2_s16", "tm2_gain_max"])
+def test_tii_on_the_warp_kernels(dm, rng, kw):
+    """With 16 or more frames in a call the warp-per-symbol kernels run for TII configurations too: the TII null symbol
+    is one constant vector per stream (phase reference carriers x the gain of the phase reference symbol), produced by
+    the general kernel on one frame and copied into every second frame (k_tii_fill).  Same frames as the general
+    kernel gives for short calls, odd stream offsets included, and as the oracle."""
+    mode = kw["mode"]
+    n = 17
+    bits = bits_for(rng, mode, n)
+    fast = dm.Modulator(max_batch=n, **kw)
+    fast.set_param("profile", 1)
+    a = fast.process_batch(bits)
+    names = [k for k, _ in fast.kernel_times()]
+    assert "k_tii_fill" in names and ("k_symbols_w" in names or "k_symbols_wg" in names), names
+    slow = dm.Modulator(max_batch=n, **kw)
+    b = np.concatenate([slow.process_batch(bits[i:i + 5]) for i in range(0, n, 5)])
+    assert a.shape == b.shape
+    for i in range(n):
+        if a.dtype == np.int16:
+            d = np.abs(a[i].astype(np.int32) - b[i].astype(np.int32))
+            assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size, i
+        else:
+            assert rel_rms(a[i], b[i]) < 1e-6, i
+    # TII frames are the even ones of the stream: after an odd number of frames the next call starts on an odd frame
+    c = fast.process_batch(bits)
+    slow2 = dm.Modulator(max_batch=n, **kw)
+    slow2.seek(n)
+    d2 = np.concatenate([slow2.process_batch(bits[i:i + 5]) for i in range(0, n, 5)])
+    null = {1: 2656, 2: 664}[mode]
+    for i in (0, 1, 2):
+        if a.dtype != np.int16:
+            assert rel_rms(c[i], d2[i]) < 1e-6, i
+        head = (null - 64) * (2 if a.dtype == np.int16 else 1)     # (a FIR reaches 44 samples into symbol 1)
+        assert (np.abs(c[i][:head]).max() > 0) == (i % 2 == 1)
+    if a.dtype != np.int16:
+        okw = dict(kw)
+        if okw.get("fir_taps") == "default":
+            okw["fir_taps"] = oracle.fir_default_taps()
+        want = oracle.OracleChain(**okw).run(bits[:3])
+        for i in range(3):
+            assert rel_rms(a[i], want[i]) < TOL, i
+
+
 @pytest.mark.parametrize("clock", [32768000, 400000000, 100000000])
 def test_cic_equalizer(dm, rng, clock):
     bits = bits_for(rng, 1, 1)
