@@ -81,6 +81,64 @@ def test_fixed_point_full_batch(dm):
     assert (energy[0::2] > 0).all() and (energy[1::2] == 0).all()
 
 
+@pytest.mark.parametrize("mode,n", [(2, 4096), (3, 4096), (4, 2048)])
+def test_config4_full_batches(dm, mode, n):
+    """configs[3] at the benchmarked batch sizes (4096 / 4096 / 2048 frames, ~45 k CTAs or one persistent grid of
+    warps): sampled frames alone == in the batch, bit for bit; host pipeline == device entry point over the whole
+    batch; sampled frames against the oracle; every frame's null symbol silent and its data symbols at the same spread."""
+    import torch
+    rng = np.random.default_rng(3000 + mode)
+    m = oracle.mode_params(mode)
+    bits = rng.integers(0, 256, (n, m.tf_bytes), dtype=np.uint8)
+    mod = dm.Modulator(mode=mode, max_batch=n)
+    mod.set_param("profile", 1)
+    d_in = torch.from_numpy(bits).cuda()
+    d_out = torch.empty(n * mod.tf_out_bytes, dtype=torch.uint8, device="cuda")
+    mod.process_batch_device(d_in.data_ptr(), n, d_out.data_ptr())
+    mod.synchronize()
+    names = [k for k, _ in mod.kernel_times()]
+    assert names == (["k_symbols"] if mode == 3 else ["k_symbols_wg"]), names
+    out = d_out.cpu().numpy().view(np.complex64).reshape(n, -1)
+    assert out.shape == (n, m.tf_samples)
+    # the same kernel on a short call (a different split of the symbols over the warps): same bits
+    few = dm.Modulator(mode=mode, max_batch=40)
+    for i0 in (0, n // 2 - 20, n - 40):
+        part = few.process_batch(bits[i0:i0 + 40])
+        assert np.array_equal(part.view(np.uint32), out[i0:i0 + 40].view(np.uint32)), i0
+    ora = oracle.OracleChain(mode=mode)
+    for i in (0, n - 1):
+        assert rel_rms(out[i], ora.process(bits[i])) < TOL, i
+    # host entry point (sliced three-stream pipeline) == device entry point, word for word
+    host = mod.process_batch(bits)
+    assert np.array_equal(host.view(np.uint32), out.view(np.uint32))
+    x = d_out.view(torch.float32).view(n, -1, 2)
+    assert float(x[:, :m.null_size - 8].abs().max()) == 0.0
+    p = (x[:, m.null_size + m.sym_size:] ** 2).sum(dim=(1, 2)) / (x.shape[1] - m.null_size - m.sym_size)
+    assert float(p.max() / p.min()) < 1.10
+
+
+@pytest.mark.parametrize("rate,n", [(8192000, 256), (10000000, 128)])
+def test_config3_5_benchmarked_batches(dm, rate, n):
+    """configs[2] / [4] at the benchmarked batch sizes (256 / 128 frames per call): the batch == the same stream in
+    calls of 100 + 1 + the rest == a second handle that seeks, bit for bit; first and last frame against the oracle."""
+    rng = np.random.default_rng(2028)
+    m = oracle.mode_params(1)
+    bits = rng.integers(0, 256, (n, m.tf_bytes), dtype=np.uint8)
+    kw = dict(mode=1, output_rate=rate, normalise=1.0 / 46000.0, fir_taps=oracle.fir_default_taps(),
+              poly=[1.0, 0.05, -0.02, 0.003, 0.0, 0.0, 0.1, -0.05, 0.01, 0.0])
+    mod = dm.Modulator(max_batch=n, **kw)
+    whole = mod.process_batch(bits).copy()
+    mod.reset()
+    parts = np.concatenate([mod.process_batch(bits[:100]), mod.process_batch(bits[100:101]), mod.process_batch(bits[101:])])
+    assert np.array_equal(parts.view(np.uint32), whole.view(np.uint32))
+    del parts
+    shard = dm.Modulator(max_batch=n, **kw)
+    shard.seek(n - 7, bits[n - 8])
+    assert np.array_equal(shard.process_batch(bits[n - 7:]).view(np.uint32), whole[n - 7:].view(np.uint32))
+    ora = oracle.OracleChain(**kw)
+    assert rel_rms(whole[0], ora.process(bits[0])) < TOL
+
+
 @pytest.mark.parametrize("rate", [10000000, 8192000])
 def test_config5_stream_in_pieces(dm, rate):
     """configs[4] / [2] geometry: FIR + resampler + MemlessPoly; 96 frames in one call == the same stream in calls of
