@@ -58,7 +58,7 @@ struct FixParams {
 
 struct FixSmem {
     uint32_t buf[FX_BUF];         // int16 pairs, fxpad layout
-    uint32_t tw[FX_POINTS];       // kiss twiddles, int16 pairs
+    uint32_t tw[FX_POINTS];       // kiss twiddles, int16 pairs, one compact table per radix-4 stage (fx_tw)
     uint32_t spread[256];
     short2 c8[8];
     short2 tail[FX_MAX_WINDOW];   // falling edge of the last symbol of the previous group
@@ -122,6 +122,15 @@ __device__ __forceinline__ void fx_bfly2(fxc &f0, fxc &f1, fxc w)
     f0 = fx_add(f0, t);
 }
 
+// Twiddles of the radix-4 stage with sub-transform size M: KISS reads tw[fs k], tw[2 fs k], tw[3 fs k] with
+// fs = N / (4 M) (kiss_fft.c kf_bfly4) -- for the early stages a stride of 64 ... 256 words, i.e. every lane of a
+// warp on the same bank (ncu, round 1: 8-way conflicts on these loads, 47 % of the kernel's shared wavefronts were
+// excess).  The same values are therefore kept stage by stage, contiguous in k: entry (q, k) of stage M at
+// fx_tw_off(M) + (q - 1) M + k.  Stage sizes are 1, 4, 16, ... or 2, 8, 32, ...; the tables of all stages below M
+// take M - 1 resp. M - 2 words, the whole set fewer than N.
+__device__ __host__ constexpr int fx_tw_off(int M) { return M - (((M & 0x55555555) != 0) ? 1 : 2); }
+__device__ __forceinline__ uint32_t fx_tw(const uint32_t *tw, int M, int q, int k) { return tw[fx_tw_off(M) + (q - 1) * M + k]; }
+
 // ---- fused passes: two KISS stages per trip through shared memory --------------------------------
 // Stages run smallest sub-transform first (kf_work's recursion unwinds that way); a butterfly of the
 // second stage needs four outputs of the first, so a thread that owns 16 points k + MA j (j < 16) of one
@@ -136,14 +145,13 @@ __device__ __forceinline__ void fx_pass_24(uint32_t *buf, const uint32_t *tw, in
     const uint4 lo = v[0], hi = v[1];
     fxc f[8] = {fx_unpack(lo.x), fx_unpack(lo.y), fx_unpack(lo.z), fx_unpack(lo.w),
                 fx_unpack(hi.x), fx_unpack(hi.y), fx_unpack(hi.z), fx_unpack(hi.w)};
-    const fxc w0 = fx_unpack(tw[0]);
+    const fxc w0 = fx_unpack(0x00007fffu);        // kiss twiddle 0: (32767, 0)
 #pragma unroll
     for (int i = 0; i < 4; i++) fx_bfly2(f[2 * i], f[2 * i + 1], w0);
-    constexpr int fsb = N / 8;
 #pragma unroll
     for (int kb = 0; kb < 2; kb++) {
         fxc g[4] = {f[kb], f[kb + 2], f[kb + 4], f[kb + 6]};
-        fx_bfly4(g, fx_unpack(tw[fsb * kb]), fx_unpack(tw[fsb * 2 * kb]), fx_unpack(tw[fsb * 3 * kb]));
+        fx_bfly4(g, fx_unpack(fx_tw(tw, 2, 1, kb)), fx_unpack(fx_tw(tw, 2, 2, kb)), fx_unpack(fx_tw(tw, 2, 3, kb)));
         f[kb] = g[0]; f[kb + 2] = g[1]; f[kb + 4] = g[2]; f[kb + 6] = g[3];
     }
     v[0] = make_uint4(fx_pack(f[0]), fx_pack(f[1]), fx_pack(f[2]), fx_pack(f[3]));
@@ -159,9 +167,8 @@ __device__ __forceinline__ void fx_pass_44(uint32_t *buf, const uint32_t *tw, in
     fxc f[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) f[j] = fx_unpack(buf[fxpad(base + j * MA)]);
-    constexpr int fsa = N / (4 * MA), fsb = N / (16 * MA);
     {
-        const fxc w1 = fx_unpack(tw[fsa * k]), w2 = fx_unpack(tw[fsa * 2 * k]), w3 = fx_unpack(tw[fsa * 3 * k]);
+        const fxc w1 = fx_unpack(fx_tw(tw, MA, 1, k)), w2 = fx_unpack(fx_tw(tw, MA, 2, k)), w3 = fx_unpack(fx_tw(tw, MA, 3, k));
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             fxc g[4] = {f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]};
@@ -173,7 +180,7 @@ __device__ __forceinline__ void fx_pass_44(uint32_t *buf, const uint32_t *tw, in
     for (int i = 0; i < 4; i++) {
         const int kb = k + i * MA;
         fxc g[4] = {f[i], f[i + 4], f[i + 8], f[i + 12]};
-        fx_bfly4(g, fx_unpack(tw[fsb * kb]), fx_unpack(tw[fsb * 2 * kb]), fx_unpack(tw[fsb * 3 * kb]));
+        fx_bfly4(g, fx_unpack(fx_tw(tw, 4 * MA, 1, kb)), fx_unpack(fx_tw(tw, 4 * MA, 2, kb)), fx_unpack(fx_tw(tw, 4 * MA, 3, kb)));
         f[i] = g[0]; f[i + 4] = g[1]; f[i + 8] = g[2]; f[i + 12] = g[3];
     }
 #pragma unroll
@@ -186,11 +193,10 @@ __device__ __forceinline__ void fx_pass_4(uint32_t *buf, const uint32_t *tw, int
 {
     const int blk = b / M, k = b % M;
     const int base = blk * 4 * M + k;
-    constexpr int fs = N / (4 * M);
     fxc g[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) g[q] = fx_unpack(buf[fxpad(base + q * M)]);
-    fx_bfly4(g, fx_unpack(tw[fs * k]), fx_unpack(tw[fs * 2 * k]), fx_unpack(tw[fs * 3 * k]));
+    fx_bfly4(g, fx_unpack(fx_tw(tw, M, 1, k)), fx_unpack(fx_tw(tw, M, 2, k)), fx_unpack(fx_tw(tw, M, 3, k)));
 #pragma unroll
     for (int q = 0; q < 4; q++) buf[fxpad(base + q * M)] = fx_pack(g[q]);
 }
@@ -254,7 +260,9 @@ __global__ void __launch_bounds__(FX_THREADS) k_symbols_fix(const __grid_constan
     const int W = p.window;
 
     // ---- per-CTA tables ----
-    for (int i = tid; i < N; i += FX_THREADS) sm.tw[i] = __ldg(reinterpret_cast<const uint32_t *>(p.tw) + i);
+    for (int M = (N == 2048 || N == 512) ? 2 : 1; 4 * M <= N; M *= 4)          // one table per radix-4 stage (fx_tw)
+        for (int i = tid; i < 3 * M; i += FX_THREADS)
+            sm.tw[fx_tw_off(M) + i] = __ldg(reinterpret_cast<const uint32_t *>(p.tw) + (N / (4 * M)) * (i / M + 1) * (i % M));
     for (int b = tid; b < 256; b += FX_THREADS) {
         uint32_t s = 0;
 #pragma unroll
