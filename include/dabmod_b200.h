@@ -210,6 +210,12 @@ const char *dabmod_b200_last_error(void);
  * dabmod_b200_process_batch copies to the host.  For callers that chain device work. */
 void *dabmod_b200_device_out(dabmod_b200 *h);
 
+/* Page-locks / releases a host range the caller owns (e.g. the memory of a reference `Buffer`, src/Buffer.cpp:
+ * 128-147), so that the copies of dabmod_b200_process_batch / _process_eti_batch into it run at PCIe speed and
+ * overlap the kernels.  Optional: pageable memory works, slower.  Unregister before the memory is freed. */
+int dabmod_b200_host_register(void *p, size_t bytes);
+int dabmod_b200_host_unregister(void *p);
+
 /* ======================================================================================
  * Row N1 of SURVEY.md section 8(f): the channel coding ahead of the path, i.e. the part of
  * DabModulator's graph between EtiReader and QpskSymbolMapper (src/DabModulator.cpp:131-150,
@@ -251,6 +257,11 @@ int dabmod_b200_coder_create(int device, int mode, const dabmod_b200_stream *str
 void dabmod_b200_coder_destroy(dabmod_b200_coder *c);
 size_t dabmod_b200_coder_tf_bytes(const dabmod_b200_coder *c);
 int dabmod_b200_coder_frames_per_tf(const dabmod_b200_coder *c);   /* BlockPartitioner d_cifCount */
+/* Byte offset of stream `stream`'s data inside a 6144-byte frame (ETI(NI) layout: SYNC, FC, NST x STC, EOH, FIC,
+ * then the subchannels in STC order; EtiReader.cpp:190-249).  The coder reads nothing else of a frame, so a caller
+ * that holds parsed sources (FicSource / SubchannelSource buffers) may place their bytes at these offsets.
+ * -1 for a bad index. */
+int dabmod_b200_coder_stream_offset(const dabmod_b200_coder *c, int stream);
 
 /* n_frames consecutive ETI frames (a multiple of frames_per_tf) -> n_frames / frames_per_tf blocks.
  * Host buffers; synchronous. */

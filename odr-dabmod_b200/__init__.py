@@ -34,10 +34,11 @@ EXPORTS = [
     "dabmod_b200_num_clipped_samples", "dabmod_b200_last_launch_count", "dabmod_b200_last_error",
     "dabmod_b200_table_interleaver", "dabmod_b200_table_phase_ref", "dabmod_b200_table_tii",
     "dabmod_b200_table_cic", "dabmod_b200_resampler_sizes", "dabmod_b200_kernel_time",
-    "dabmod_b200_device_out",
+    "dabmod_b200_device_out", "dabmod_b200_host_register", "dabmod_b200_host_unregister",
     # row N1: channel coding
     "dabmod_b200_eti_describe", "dabmod_b200_coder_create", "dabmod_b200_coder_destroy",
-    "dabmod_b200_coder_tf_bytes", "dabmod_b200_coder_frames_per_tf", "dabmod_b200_coder_process",
+    "dabmod_b200_coder_tf_bytes", "dabmod_b200_coder_frames_per_tf", "dabmod_b200_coder_stream_offset",
+    "dabmod_b200_coder_process",
     "dabmod_b200_coder_process_device", "dabmod_b200_coder_reset", "dabmod_b200_coder_prime",
     "dabmod_b200_process_eti_batch", "dabmod_b200_process_eti_batch_to_fd", "dabmod_b200_seek_eti",
     "dabmod_b200_coder_last_error",

@@ -2,6 +2,7 @@
  * kernels behind dabmod_b200_process(). */
 #include "B200OfdmChain.h"
 
+#include <algorithm>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -68,7 +69,7 @@ int load_coefs(const std::string& file, std::vector<float>& coefs)
 } // namespace
 
 B200OfdmChain::B200OfdmChain(mod_settings_t& s, const std::string& format, int device, bool fixedPoint,
-                             int pipelineDepth) :
+                             int pipelineDepth, int maxBatch) :
     ModCodec(),
     RemoteControllable("b200chain"),
     m_settings(s),
@@ -94,7 +95,8 @@ B200OfdmChain::B200OfdmChain(mod_settings_t& s, const std::string& format, int d
     c.tii_pattern = s.tiiConfig.pattern;
     c.tii_old_variant = s.tiiConfig.old_variant;
     /* the fixed-point chain of DabModulator.cpp:144,194-224 (fftEngine = KISS there) */
-    if (fixedPoint || s.fftEngine == FFTEngine::KISS) c.fft_engine = DABMOD_B200_FFT_KISS_FIXED;
+    if (fixedPoint || s.fftEngine == FFTEngine::KISS || static_cast<int>(s.fftEngine) == 4 /* b200_fixed */ ||
+        static_cast<int>(s.fftEngine) == 6 /* b200_eti_fixed */) c.fft_engine = DABMOD_B200_FFT_KISS_FIXED;
 
     std::vector<float> taps, coefs;
     if (!s.filterTapsFilename.empty()) {
@@ -111,7 +113,7 @@ B200OfdmChain::B200OfdmChain(mod_settings_t& s, const std::string& format, int d
     else if (format == "u8") c.format = DABMOD_B200_FMT_U8;
     else if (format == "s8") c.format = DABMOD_B200_FMT_S8;
     else throw std::runtime_error("FormatConverter: Invalid format " + format);
-    c.max_batch = m_depth > 0 ? (int32_t)m_depth : 1;
+    c.max_batch = std::max<int32_t>(m_depth > 0 ? (int32_t)m_depth : 1, maxBatch);
 
     if (dabmod_b200_create(&c, &m_handle) != DABMOD_B200_OK) fail("create");
     if (m_depth > 0) {

@@ -70,8 +70,10 @@ public:
      * control changes are written back into it, so they survive a modulator restart like those of the blocks
      * that hold references into it (src/GainControl.h:72-77, src/OfdmGenerator.h:50-56, src/TII.h:82,
      * src/GuardIntervalInserter.h:48-54). */
+    /* maxBatch: the largest batch the handle must take (dabmod_b200_config.max_batch), for callers that drive the
+     * handle's batch entry points themselves (B200EtiChain); process() needs max(1, pipelineDepth). */
     B200OfdmChain(mod_settings_t& settings, const std::string& format, int device = 0,
-                  bool fixedPoint = false, int pipelineDepth = 0);
+                  bool fixedPoint = false, int pipelineDepth = 0, int maxBatch = 0);
     virtual ~B200OfdmChain();
     B200OfdmChain(const B200OfdmChain&) = delete;
     B200OfdmChain& operator=(const B200OfdmChain&) = delete;
@@ -90,6 +92,9 @@ public:
 
     /* the "tii" controllable (enrol it next to the chain: rcs.enrol(chain->tii_control())) */
     RemoteControllable* tii_control() { return &m_tii; }
+
+    /* the C-ABI handle behind the chain (include/dabmod_b200.h) */
+    dabmod_b200* handle() const { return m_handle; }
 
 private:
     dabmod_b200* m_handle = nullptr;

@@ -437,6 +437,10 @@ int dabmod_b200_coder_create(int device, int mode, const dabmod_b200_stream *st,
 
 size_t dabmod_b200_coder_tf_bytes(const dabmod_b200_coder *c) { return c ? (size_t)c->tf_bytes : 0; }
 int dabmod_b200_coder_frames_per_tf(const dabmod_b200_coder *c) { return c ? c->cif_count : 0; }
+int dabmod_b200_coder_stream_offset(const dabmod_b200_coder *c, int stream)
+{
+    return c && stream >= 0 && stream < (int)c->streams.size() ? c->streams[stream].in_off : -1;
+}
 
 // Encodes n_frames device-resident ETI frames into the ring (and, unless bits == nullptr, assembles
 // the transmission-frame blocks).  Caller holds the lock.

@@ -1506,6 +1506,22 @@ int dabmod_b200_seek(dabmod_b200 *h, uint64_t tf_index, const uint8_t *prev_bits
 
 void *dabmod_b200_device_out(dabmod_b200 *h) { return h ? (void *)h->d_out.p : nullptr; }
 
+int dabmod_b200_host_register(void *p, size_t bytes)
+{
+    return guard([&] {
+        if (!p || !bytes) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        CUDA_CHECK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    });
+}
+
+int dabmod_b200_host_unregister(void *p)
+{
+    return guard([&] {
+        if (!p) throw ApiError(DABMOD_B200_EINVAL, "null argument");
+        CUDA_CHECK(cudaHostUnregister(p));
+    });
+}
+
 uint64_t dabmod_b200_num_clipped_samples(dabmod_b200 *h)
 {
     if (!h) return 0;

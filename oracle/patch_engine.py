@@ -40,20 +40,22 @@ def main():
     c = edit(c, '    else if (fft_engine_minuscule == "dexter") {\n        return FFTEngine::DEXTER;\n    }\n',
              '    else if (fft_engine_minuscule == "dexter") {\n        return FFTEngine::DEXTER;\n    }\n'
              '    else if (fft_engine_minuscule == "b200") {\n        return FFTENGINE_B200;\n    }\n'
-             '    else if (fft_engine_minuscule == "b200_fixed") {\n        return FFTENGINE_B200_FIXED;\n    }\n',
+             '    else if (fft_engine_minuscule == "b200_fixed") {\n        return FFTENGINE_B200_FIXED;\n    }\n'
+             '    else if (fft_engine_minuscule == "b200_eti") {\n        return FFTENGINE_B200_ETI;\n    }\n'
+             '    else if (fft_engine_minuscule == "b200_eti_fixed") {\n        return FFTENGINE_B200_ETI_FIXED;\n    }\n',
              "ConfigParser.cpp")
-    c = edit(c, '#include "ConfigParser.h"\n', '#include "ConfigParser.h"\n#include "B200OfdmChain.h"\n', "ConfigParser.cpp")
+    c = edit(c, '#include "ConfigParser.h"\n', '#include "ConfigParser.h"\n#include "B200EtiChain.h"\n', "ConfigParser.cpp")
     save("ConfigParser.cpp", c)
 
     m = load("src/DabModulator.cpp")
-    m = edit(m, '#include "DabModulator.h"\n', '#include "DabModulator.h"\n#include "B200OfdmChain.h"\n#include <cstdlib>\n',
+    m = edit(m, '#include "DabModulator.h"\n', '#include "DabModulator.h"\n#include "B200EtiChain.h"\n#include <cstdlib>\n',
              "DabModulator.cpp")
     m = edit(m, "        const bool fixedPoint = m_settings.fftEngine != FFTEngine::FFTW;\n",
-             "        const bool b200 = m_settings.fftEngine == FFTENGINE_B200 or m_settings.fftEngine == FFTENGINE_B200_FIXED;\n"
+             "        const bool b200 = b200_engine(m_settings.fftEngine);\n"
              "        // With a B200 engine the CPU blocks below are still constructed, as for the engine whose chain the\n"
              "        // GPU restates, but never wired: BlockPartitioner feeds the B200OfdmChain instead (see the end).\n"
-             "        const FFTEngine engine = m_settings.fftEngine == FFTENGINE_B200 ? FFTEngine::FFTW :\n"
-             "            m_settings.fftEngine == FFTENGINE_B200_FIXED ? FFTEngine::KISS : m_settings.fftEngine;\n"
+             "        const FFTEngine engine = not b200 ? m_settings.fftEngine :\n"
+             "            b200_engine_is_fixed(m_settings.fftEngine) ? FFTEngine::KISS : FFTEngine::FFTW;\n"
              "        const bool fixedPoint = engine != FFTEngine::FFTW;\n", "DabModulator.cpp")
     m = edit(m, "        switch (m_settings.fftEngine) {\n", "        switch (engine) {\n", "DabModulator.cpp")
     m = edit(m, "                m_settings.ofdmWindowOverlap, m_settings.fftEngine);\n",
@@ -67,7 +69,7 @@ def main():
              "            // the whole chain behind BlockPartitioner on the GPU; ODR_DABMOD_B200_DEPTH = TFs per batch\n"
              "            const char *depth = getenv(\"ODR_DABMOD_B200_DEPTH\");\n"
              "            auto chain = make_shared<B200OfdmChain>(m_settings, m_format, 0,\n"
-             "                    m_settings.fftEngine == FFTENGINE_B200_FIXED, depth ? atoi(depth) : 0);\n"
+             "                    b200_engine_is_fixed(m_settings.fftEngine), depth ? atoi(depth) : 0);\n"
              "            rcs.enrol(chain.get());\n"
              "            rcs.enrol(chain->tii_control());\n"
              "            m_flowgraph->connect(cifPart, chain);\n"
@@ -76,17 +78,35 @@ def main():
              "        else {\n"
              "        m_flowgraph->connect(cifPart, cifMap);\n", "DabModulator.cpp")
     m = edit(m, '        etiLog.level(debug) << "DabModulator set up.";\n',
-             '        }\n        etiLog.level(debug) << "DabModulator set up.";\n', "DabModulator.cpp")
+             '        }\n        }\n        etiLog.level(debug) << "DabModulator set up.";\n', "DabModulator.cpp")
+    m = edit(m, "        m_flowgraph = make_shared<Flowgraph>(m_settings.showProcessTime);\n",
+             "        m_flowgraph = make_shared<Flowgraph>(m_settings.showProcessTime);\n"
+             "        if (b200_engine_is_eti(m_settings.fftEngine)) {\n"
+             "            // channel coding + OFDM chain on the GPU: the graph is B200EtiChain -> (OutputMemory);\n"
+             "            // ODR_DABMOD_B200_DEPTH = transmission frames per batch (default 64)\n"
+             "            const char *depth = getenv(\"ODR_DABMOD_B200_DEPTH\");\n"
+             "            auto eti = make_shared<B200EtiChain>(m_etiSource, m_settings, m_format, 0,\n"
+             "                    b200_engine_is_fixed(m_settings.fftEngine), depth and atoi(depth) > 0 ? atoi(depth) : 64);\n"
+             "            rcs.enrol(&eti->chain());\n"
+             "            rcs.enrol(eti->chain().tii_control());\n"
+             "            m_output = make_shared<B200SwapOutput>(dataOut);\n"
+             "            m_flowgraph->connect(eti, m_output);\n"
+             "        }\n"
+             "        else {\n", "DabModulator.cpp")
     save("DabModulator.cpp", m)
 
     d = load("src/DabMod.cpp")
     d = edit(d, "    if (s.useFileOutput) {\n        if (s.fftEngine != FFTEngine::FFTW) {",
-             "    if (s.useFileOutput) {\n        if (s.fftEngine != FFTEngine::FFTW and s.fftEngine != FFTENGINE_B200) {",
+             "    if (s.useFileOutput) {\n        if (s.fftEngine != FFTEngine::FFTW and s.fftEngine != FFTENGINE_B200 and s.fftEngine != FFTENGINE_B200_ETI) {",
              "DabMod.cpp")
     d = edit(d, "    if (mod_settings.fftEngine == FFTEngine::KISS) {\n        output_format = \"\";",
-             "    if (mod_settings.fftEngine == FFTEngine::KISS or mod_settings.fftEngine == FFTENGINE_B200_FIXED) {\n"
+             "    if (mod_settings.fftEngine == FFTEngine::KISS or b200_engine_is_fixed(mod_settings.fftEngine)) {\n"
              "        output_format = \"\";", "DabMod.cpp")
-    d = edit(d, '#include "ConfigParser.h"\n', '#include "ConfigParser.h"\n#include "B200OfdmChain.h"\n', "DabMod.cpp")
+    d = edit(d, '#include "ConfigParser.h"\n', '#include "ConfigParser.h"\n#include "B200EtiChain.h"\n', "DabMod.cpp")
+    # end of the input file: the ETI engines still hold the frames of an unfinished batch
+    d = edit(d, '                        etiLog.level(info) << "End of file reached.";\n',
+             '                        etiLog.level(info) << "End of file reached.";\n'
+             '                        if (B200EtiChain::flush_active()) m.flowgraph->run();\n', "DabMod.cpp")
     save("DabMod.cpp", d)
     print("patch_engine: wrote ConfigParser.cpp DabModulator.cpp DabMod.cpp to", out)
 

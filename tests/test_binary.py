@@ -149,3 +149,48 @@ def test_b200_engine_in_the_real_binary(tmp_path, case):
                 assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size, (case, depth, i)
             else:
                 assert rel_rms(a[i], b[i]) < 2e-6, (case, depth, i)
+
+
+ETI_CASES = {
+    # name: (case of CASES, engine)
+    "c1_native": "b200_eti",
+    "c2_fir": "b200_eti",
+    "c3_fir_res_poly": "b200_eti",
+    "tm2_s16_tii": "b200_eti",
+    "fixed_tm1": "b200_eti_fixed",
+    "fixed_tm4_window": "b200_eti_fixed",
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have, reason="oracle/_ref binaries not built (make -C oracle binary)")
+@pytest.mark.parametrize("case", sorted(ETI_CASES))
+def test_eti_engine_in_the_real_binary(tmp_path, case):
+    """`fft_engine = b200_eti[_fixed]`: DabModulator's graph is ONE node, B200EtiChain (channel coding + OFDM chain on
+    the GPU, fed from the sources EtiReader has parsed), batches of `depth` TFs, the unfinished batch flushed at the
+    end of the file.  Every TF of the input comes out; the ones the reference wrote must agree."""
+    mode, n_tf, ref_engine, _, dt, P, kw = CASES[case]
+    if kw.get("poly"):
+        kw = dict(kw, polyfile=str(tmp_path / "poly.coef"))
+        write_poly_file(kw["polyfile"], [1.0, 0.05, -0.02, 0.0, 0.0], [0.0, 0.1, -0.05, 0.0, 0.0])
+    eti_path = make_eti(tmp_path, mode, n_tf)
+    ref = np.fromfile(run_binary(REF_BIN, tmp_path, "ref", eti_path, ref_engine, **kw), dt)
+    per_tf = ref.size // (n_tf - P)
+    outs = []
+    for depth in (2, 4, 64):
+        got = np.fromfile(run_binary(B200_BIN, tmp_path, "eti_d%d" % depth, eti_path, ETI_CASES[case], depth=depth, **kw), dt)
+        assert got.size == n_tf * per_tf, (got.size / per_tf, n_tf)
+        outs.append(got)
+        n = n_tf - P
+        a, b = got[:n * per_tf].reshape(n, per_tf), ref.reshape(n, per_tf)
+        for i in range(n):
+            if ref_engine == "kiss":
+                assert np.array_equal(a[i], b[i]), (case, depth, i)
+            elif dt is np.int16:
+                d = np.abs(a[i].astype(np.int32) - b[i].astype(np.int32))
+                assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size, (case, depth, i)
+            else:
+                assert rel_rms(a[i], b[i]) < 2e-6, (case, depth, i)
+    # the batch size changes nothing
+    # (gain mode var: per-symbol statistics; the resampler state is carried across batches)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), case
