@@ -389,22 +389,57 @@ def measure_binary(n_frames=4000):
            "[output]\noutput=file\n[fileoutput]\nformat=complexf\nfilename=/dev/null\n")
     res = {"workload": "c0 TM I, ETI file input, native 2.048 Msps, no FIR/resample, file output: the real binary",
            "eti_frames": n_frames}
-    for key, binary, engine, depth in (("reference_binary", ref_bin, "fftw", 0), ("b200_binary", b200_bin, "b200", 0),
-                                       ("b200_binary_depth64", b200_bin, "b200", 64)):
+    # the long input: the same file ten times over (4000 frames = 16 FCT periods, so the frame counter stays continuous)
+    long_path, long_n = os.path.join(tmp, "in_long.eti"), 10 * n_frames
+    with open(path, "rb") as f:
+        blob = f.read()
+    with open(long_path, "wb") as f:
+        for _ in range(10):
+            f.write(blob)
+    del blob
+    out_file = os.path.join(tmp, "out.iq")
+    runs = (
+        # key, binary, engine, depth, input, frames, format, output
+        ("reference_binary", ref_bin, "fftw", 0, path, n_frames, "complexf", "/dev/null"),
+        ("b200_binary", b200_bin, "b200", 0, path, n_frames, "complexf", "/dev/null"),
+        ("b200_binary_depth64", b200_bin, "b200", 64, path, n_frames, "complexf", "/dev/null"),
+        ("b200_eti_binary", b200_bin, "b200_eti", 64, path, n_frames, "complexf", "/dev/null"),
+        ("b200_eti_binary_long", b200_bin, "b200_eti", 256, long_path, long_n, "complexf", "/dev/null"),
+        ("b200_eti_binary_long_s16", b200_bin, "b200_eti", 256, long_path, long_n, "s16", "/dev/null"),
+        ("b200_eti_binary_long_u8", b200_bin, "b200_eti", 256, long_path, long_n, "u8", "/dev/null"),
+        ("reference_binary_to_file", ref_bin, "fftw", 0, path, n_frames, "complexf", out_file),
+        ("b200_eti_binary_to_file", b200_bin, "b200_eti", 64, path, n_frames, "complexf", out_file),
+    )
+    for key, binary, engine, depth, src, nfr, fmt, dst in runs:
         cfg = os.path.join(tmp, key + ".ini")
         with open(cfg, "w") as f:
-            f.write(ini % (path, engine))
-        env = dict(os.environ, ODR_DABMOD_B200_DEPTH=str(depth))
+            f.write((ini % (src, engine)).replace("format=complexf", "format=" + fmt).replace("filename=/dev/null",
+                                                                                             "filename=" + dst))
+        env = dict(os.environ, ODR_DABMOD_B200_DEPTH=str(depth), ODR_DABMOD_B200_TRACE="1")
         try:
             t0 = time.perf_counter()
-            r = subprocess.run([binary, cfg], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+            r = subprocess.run([binary, cfg], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                               timeout=300)
             dt = time.perf_counter() - t0
-            res[key] = {"eti_frames_per_s": n_frames / dt, "seconds": dt, "returncode": r.returncode}
+            res[key] = {"eti_frames_per_s": nfr / dt, "seconds": dt, "eti_frames": nfr, "returncode": r.returncode}
+            # the ETI engines report the time from the first frame to the end of the stream (ODR_DABMOD_B200_TRACE):
+            # the rate without process start-up and CUDA context creation (0.7 - 2.8 s, as large as the run itself)
+            import re
+            m = re.search(r"B200EtiChain: (\d+) frames in ([0-9.]+) s since the first frame", r.stdout)
+            if m and float(m.group(2)) > 0:
+                res[key]["eti_frames_per_s_streaming"] = int(m.group(1)) / float(m.group(2))
         except Exception as e:
             res[key] = {"error": "%s: %s" % (type(e).__name__, e)}
-    res["note"] = ("wall clock of the whole process incl. start-up (CUDA context creation ~0.3 s for the b200 arm); "
-                   "both arms are bound by the reference's single-threaded EtiReader + channel coding "
-                   "(~0.25 ms per ETI frame), which the engine does not replace")
+        if dst != "/dev/null" and os.path.exists(dst):
+            res[key]["output_bytes"] = os.path.getsize(dst)
+            os.remove(dst)
+    res["note"] = ("wall clock of the whole process incl. start-up (CUDA context creation ~0.3 s for the b200 arms); "
+                   "reference_binary and b200_binary are bound by the reference's single-threaded EtiReader + channel "
+                   "coding (~0.25 ms per ETI frame); b200_eti = fft_engine b200_eti: coding and chain on the GPU, "
+                   "the host keeps InputFileReader, EtiReader and OutputFile (the *_to_file runs write a real file in "
+                   "the temporary directory)")
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
     return res
 
 

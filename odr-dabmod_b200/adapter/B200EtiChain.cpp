@@ -3,6 +3,9 @@
 #include "B200EtiChain.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -46,8 +49,13 @@ B200EtiChain::B200EtiChain(EtiSource& etiSource, mod_settings_t& settings, const
     ModInput(),
     m_eti(etiSource),
     m_device(device),
-    m_batch(batchTfs > 0 ? (size_t)batchTfs : 1)
+    m_batch(batchTfs > 0 ? (size_t)batchTfs : 1),
+    m_mode(settings.dabMode)
 {
+    /* DabModulator::setMode (src/DabModulator.cpp:84-126) */
+    if (m_mode < 1 or m_mode > 4) throw std::runtime_error("DabModulator::setMode invalid mode size");
+    m_trace = getenv("ODR_DABMOD_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     m_chain.reset(new B200OfdmChain(settings, format, device, fixedPoint, 0, (int)m_batch));
     /* process() returns the byte count as an int */
     const size_t out_tf = dabmod_b200_tf_out_bytes(m_chain->handle());
@@ -56,13 +64,30 @@ B200EtiChain::B200EtiChain(EtiSource& etiSource, mod_settings_t& settings, const
         m_chain.reset(new B200OfdmChain(settings, format, device, fixedPoint, 0, (int)m_batch));
     }
     g_active = this;
+    if (m_trace) {
+        fprintf(stderr, "B200EtiChain: modulator handle for batches of %zu TFs created in %.3f s\n", m_batch,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
 }
 
 B200EtiChain::~B200EtiChain()
 {
     if (g_active == this) g_active = nullptr;
+    if (m_trace) {
+        fprintf(stderr, "B200EtiChain: %zu frames in %.3f s since the first frame\n", m_n_frames,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - m_t_first).count());
+        fprintf(stderr, "B200EtiChain: %zu frames collected in %.3f s, %zu batches in %.3f s on the GPU path "
+                        "(%zu host ranges page-locked in %.3f s)\n",
+                m_n_frames, m_t_collect, m_n_batches, m_t_gpu, m_pinned.size(), m_t_pin);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
     for (auto& p : m_pinned) dabmod_b200_host_unregister(p.first);
     dabmod_b200_coder_destroy(m_coder);
+    m_chain.reset();
+    if (m_trace) {
+        fprintf(stderr, "B200EtiChain: released in %.3f s\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
 }
 
 bool B200EtiChain::flush()
@@ -81,7 +106,7 @@ bool B200EtiChain::flush_active()
  * 300-383, from the sources the EtiSource has built for this multiplex */
 void B200EtiChain::build_coder()
 {
-    const unsigned mode = m_eti.getMode();
+    const unsigned mode = m_mode;       /* the configured mode, like DabModulator::process (src/DabModulator.cpp:133) */
     std::vector<dabmod_b200_stream> streams;
     auto fic = m_eti.getFic();
     streams.push_back(describe(fic->getFramesize(), mode == 3 ? 384 : 288, 0, fic->get_rules()));
@@ -131,14 +156,20 @@ void B200EtiChain::pin(Buffer* dataOut, size_t need)
     dataOut->setLength(0);                  /* nothing to carry over into a new allocation */
     dataOut->setLength(need);
     /* a full batch only: the short batch of a flush does not justify a registration */
-    if (need == m_batch * dabmod_b200_tf_out_bytes(m_chain->handle()) and
-        dabmod_b200_host_register(dataOut->getData(), need) == DABMOD_B200_OK) {
-        m_pinned.push_back({dataOut->getData(), need});
+    if (need == m_batch * dabmod_b200_tf_out_bytes(m_chain->handle())) {
+        if (dabmod_b200_host_register(dataOut->getData(), need) == DABMOD_B200_OK) {
+            m_pinned.push_back({dataOut->getData(), need});
+        }
+        else if (m_trace) fprintf(stderr, "B200EtiChain: host_register: %s\n", dabmod_b200_last_error());
     }
 }
 
 int B200EtiChain::process(Buffer* dataOut)
 {
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
+    if (m_n_frames == 0) m_t_first = t0;
+    auto since = [](clk::time_point t) { return std::chrono::duration<double>(clk::now() - t).count(); };
     if (not m_flush) {
         if (not m_coder) build_coder();
         else if (not same_multiplex()) {
@@ -159,6 +190,8 @@ int B200EtiChain::process(Buffer* dataOut)
             memcpy(frame + m_offsets[i++], m_tmp.getData(), m_tmp.getLength());
         }
         m_collected++;
+        m_n_frames++;
+        m_t_collect += since(t0);
     }
 
     const bool full = m_collected == m_batch * m_cif;
@@ -173,12 +206,17 @@ int B200EtiChain::process(Buffer* dataOut)
         return 0;
     }
     const size_t need = n_tf * dabmod_b200_tf_out_bytes(m_chain->handle());
+    const auto t1 = clk::now();
     pin(dataOut, need);
+    m_t_pin += since(t1);
+    const auto t2 = clk::now();
     size_t nb = 0;
     if (dabmod_b200_process_eti_batch(m_chain->handle(), m_coder, m_frames.data(), n_frames, dataOut->getData(),
                                       dataOut->getLength(), &nb) != DABMOD_B200_OK) {
         fail("process_eti_batch", dabmod_b200_coder_last_error());
     }
+    m_t_gpu += since(t2);
+    m_n_batches++;
     /* frames of an incomplete TF (only after a flush) stay for the next batch */
     const size_t rest = m_collected - n_frames;
     if (rest) memmove(m_frames.data(), m_frames.data() + n_frames * ETI_FRAME, rest * ETI_FRAME);

@@ -26,6 +26,7 @@
  */
 #pragma once
 
+#include <chrono>
 #include <memory>
 #include <string>
 #include <utility>
@@ -87,6 +88,12 @@ private:
     dabmod_b200_coder* m_coder = nullptr;
     int m_device;
     size_t m_batch;                 /* TFs per batch */
+    unsigned m_mode;
+    /* ODR_DABMOD_B200_TRACE: where the time went, printed at destruction */
+    bool m_trace = false;
+    double m_t_collect = 0, m_t_gpu = 0, m_t_pin = 0;
+    size_t m_n_frames = 0, m_n_batches = 0;
+    std::chrono::steady_clock::time_point m_t_first;
     size_t m_cif = 0;               /* ETI frames per TF */
     size_t m_collected = 0;         /* frames in m_frames */
     bool m_flush = false;
