@@ -389,12 +389,12 @@ def measure_binary(n_frames=4000):
            "[output]\noutput=file\n[fileoutput]\nformat=complexf\nfilename=/dev/null\n")
     res = {"workload": "c0 TM I, ETI file input, native 2.048 Msps, no FIR/resample, file output: the real binary",
            "eti_frames": n_frames}
-    # the long input: the same file ten times over (4000 frames = 16 FCT periods, so the frame counter stays continuous)
-    long_path, long_n = os.path.join(tmp, "in_long.eti"), 10 * n_frames
+    # the long input: the same file thirty times over (4000 frames = 16 FCT periods, so the frame counter stays continuous)
+    long_path, long_n = os.path.join(tmp, "in_long.eti"), 30 * n_frames
     with open(path, "rb") as f:
         blob = f.read()
     with open(long_path, "wb") as f:
-        for _ in range(10):
+        for _ in range(30):
             f.write(blob)
     del blob
     out_file = os.path.join(tmp, "out.iq")
@@ -404,9 +404,9 @@ def measure_binary(n_frames=4000):
         ("b200_binary", b200_bin, "b200", 0, path, n_frames, "complexf", "/dev/null"),
         ("b200_binary_depth64", b200_bin, "b200", 64, path, n_frames, "complexf", "/dev/null"),
         ("b200_eti_binary", b200_bin, "b200_eti", 64, path, n_frames, "complexf", "/dev/null"),
-        ("b200_eti_binary_long", b200_bin, "b200_eti", 256, long_path, long_n, "complexf", "/dev/null"),
-        ("b200_eti_binary_long_s16", b200_bin, "b200_eti", 256, long_path, long_n, "s16", "/dev/null"),
-        ("b200_eti_binary_long_u8", b200_bin, "b200_eti", 256, long_path, long_n, "u8", "/dev/null"),
+        ("b200_eti_binary_long", b200_bin, "b200_eti", 64, long_path, long_n, "complexf", "/dev/null"),
+        ("b200_eti_binary_long_s16", b200_bin, "b200_eti", 64, long_path, long_n, "s16", "/dev/null"),
+        ("b200_eti_binary_long_u8", b200_bin, "b200_eti", 64, long_path, long_n, "u8", "/dev/null"),
         ("reference_binary_to_file", ref_bin, "fftw", 0, path, n_frames, "complexf", out_file),
         ("b200_eti_binary_to_file", b200_bin, "b200_eti", 64, path, n_frames, "complexf", out_file),
     )

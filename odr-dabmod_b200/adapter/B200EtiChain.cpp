@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <stdexcept>
 
 #include "FicSource.h"
@@ -55,6 +56,7 @@ B200EtiChain::B200EtiChain(EtiSource& etiSource, mod_settings_t& settings, const
     /* DabModulator::setMode (src/DabModulator.cpp:84-126) */
     if (m_mode < 1 or m_mode > 4) throw std::runtime_error("DabModulator::setMode invalid mode size");
     m_trace = getenv("ODR_DABMOD_B200_TRACE") != nullptr;
+    m_async = getenv("ODR_DABMOD_B200_SYNC") == nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     m_chain.reset(new B200OfdmChain(settings, format, device, fixedPoint, 0, (int)m_batch));
     /* process() returns the byte count as an int */
@@ -73,12 +75,15 @@ B200EtiChain::B200EtiChain(EtiSource& etiSource, mod_settings_t& settings, const
 B200EtiChain::~B200EtiChain()
 {
     if (g_active == this) g_active = nullptr;
+    if (m_job.valid()) {
+        try { m_job.get(); } catch (...) {}
+    }
     if (m_trace) {
         fprintf(stderr, "B200EtiChain: %zu frames in %.3f s since the first frame\n", m_n_frames,
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - m_t_first).count());
-        fprintf(stderr, "B200EtiChain: %zu frames collected in %.3f s, %zu batches in %.3f s on the GPU path "
-                        "(%zu host ranges page-locked in %.3f s)\n",
-                m_n_frames, m_t_collect, m_n_batches, m_t_gpu, m_pinned.size(), m_t_pin);
+        fprintf(stderr, "B200EtiChain: %zu frames collected in %.3f s, %zu batches in %.3f s on the GPU path, of "
+                        "which the caller waited %.3f s (%zu host ranges page-locked in %.3f s)\n",
+                m_n_frames, m_t_collect, m_n_batches, m_t_gpu, m_t_wait, m_pinned.size(), m_t_pin);
     }
     const auto t0 = std::chrono::steady_clock::now();
     for (auto& p : m_pinned) dabmod_b200_host_unregister(p.first);
@@ -92,7 +97,7 @@ B200EtiChain::~B200EtiChain()
 
 bool B200EtiChain::flush()
 {
-    if (m_cif == 0 or m_collected < m_cif) return false;
+    if (not m_job.valid() and (m_cif == 0 or m_collected < m_cif)) return false;
     m_flush = true;
     return true;
 }
@@ -122,7 +127,7 @@ void B200EtiChain::build_coder()
     }
     m_offsets.resize(streams.size());
     for (size_t i = 0; i < streams.size(); i++) m_offsets[i] = dabmod_b200_coder_stream_offset(m_coder, (int)i);
-    m_frames.assign(m_batch * m_cif * ETI_FRAME, 0);
+    m_collecting.assign(m_batch * m_cif * ETI_FRAME, 0);
 }
 
 bool B200EtiChain::same_multiplex() const
@@ -138,30 +143,83 @@ bool B200EtiChain::same_multiplex() const
     return true;
 }
 
-/* Page-locks the storage the batch is about to land in.  B200SwapOutput makes the graph's two Buffers alternate,
- * each keeps its storage once it has the size of a batch (Buffer::setLength only reallocates to grow,
- * src/Buffer.cpp:128-147), so at most two ranges are registered, each once. */
-void B200EtiChain::pin(Buffer* dataOut, size_t need)
+/* Sizes and page-locks the Buffer a batch is about to land in.  The storages circulate: a finished batch is swapped
+ * into the graph's edge Buffer, B200SwapOutput swaps that with DabModulator's output Buffer, and what comes back is
+ * the storage of an older batch -- each keeps its size (Buffer::setLength only reallocates to grow,
+ * src/Buffer.cpp:128-147), so at most four ranges are registered, each once. */
+void B200EtiChain::pin(Buffer& buf, size_t need)
 {
     auto it = std::find_if(m_pinned.begin(), m_pinned.end(),
-                           [&](const std::pair<void*, size_t>& p) { return p.first == dataOut->getData(); });
+                           [&](const std::pair<void*, size_t>& p) { return p.first == buf.getData(); });
     if (it != m_pinned.end() and it->second >= need) {
-        dataOut->setLength(need);
+        buf.setLength(need);
         return;
     }
     if (it != m_pinned.end()) {             /* registered, too small: release it before setLength frees it */
         dabmod_b200_host_unregister(it->first);
         m_pinned.erase(it);
     }
-    dataOut->setLength(0);                  /* nothing to carry over into a new allocation */
-    dataOut->setLength(need);
+    buf.setLength(0);                       /* nothing to carry over into a new allocation */
+    buf.setLength(need);
     /* a full batch only: the short batch of a flush does not justify a registration */
     if (need == m_batch * dabmod_b200_tf_out_bytes(m_chain->handle())) {
-        if (dabmod_b200_host_register(dataOut->getData(), need) == DABMOD_B200_OK) {
-            m_pinned.push_back({dataOut->getData(), need});
+        if (dabmod_b200_host_register(buf.getData(), need) == DABMOD_B200_OK) {
+            m_pinned.push_back({buf.getData(), need});
         }
         else if (m_trace) fprintf(stderr, "B200EtiChain: host_register: %s\n", dabmod_b200_last_error());
     }
+}
+
+/* Hands the collected whole transmission frames to the GPU: the call runs on a worker thread while the caller
+ * reads and parses the frames of the next batch (the N-TF form of PipelinedModCodec, src/ModPlugin.cpp:90-115). */
+void B200EtiChain::launch()
+{
+    using clk = std::chrono::steady_clock;
+    const size_t n_tf = m_collected / m_cif, n_frames = n_tf * m_cif;
+    if (n_tf == 0) return;
+    const int slot = m_next_slot;
+    m_next_slot ^= 1;
+    const auto t1 = clk::now();
+    pin(m_out[slot], n_tf * dabmod_b200_tf_out_bytes(m_chain->handle()));
+    m_t_pin += std::chrono::duration<double>(clk::now() - t1).count();
+    m_frames[slot].swap(m_collecting);                  /* the batch's frames; m_collecting takes the free array */
+    if (m_collecting.size() != m_frames[slot].size()) m_collecting.assign(m_frames[slot].size(), 0);
+    /* frames of an incomplete TF (only after a flush) open the next batch */
+    const size_t rest = m_collected - n_frames;
+    if (rest) memcpy(m_collecting.data(), m_frames[slot].data() + n_frames * ETI_FRAME, rest * ETI_FRAME);
+    m_collected = rest;
+    m_job_meta = std::move(m_meta);
+    m_meta.clear();
+    m_job_slot = slot;
+    const uint8_t* frames = m_frames[slot].data();
+    Buffer* out = &m_out[slot];
+    m_job = std::async(std::launch::async, [this, frames, n_frames, out]() -> double {
+        const auto t2 = clk::now();
+        size_t nb = 0;
+        if (dabmod_b200_process_eti_batch(m_chain->handle(), m_coder, frames, n_frames, out->getData(),
+                                          out->getLength(), &nb) != DABMOD_B200_OK) {
+            fail("process_eti_batch", dabmod_b200_coder_last_error());
+        }
+        out->setLength(nb);
+        return std::chrono::duration<double>(clk::now() - t2).count();
+    });
+}
+
+/* the finished batch (waits for it), swapped into dataOut; 0 when none is in flight */
+int B200EtiChain::collect(Buffer* dataOut)
+{
+    if (not m_job.valid()) {
+        dataOut->setLength(0);
+        return 0;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    m_t_gpu += m_job.get();                             /* rethrows what the worker threw */
+    m_t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    m_n_batches++;
+    dataOut->swap(m_out[m_job_slot]);
+    m_meta_out = std::move(m_job_meta);
+    m_job_meta.clear();
+    return (int)dataOut->getLength();
 }
 
 int B200EtiChain::process(Buffer* dataOut)
@@ -169,62 +227,44 @@ int B200EtiChain::process(Buffer* dataOut)
     using clk = std::chrono::steady_clock;
     const auto t0 = clk::now();
     if (m_n_frames == 0) m_t_first = t0;
-    auto since = [](clk::time_point t) { return std::chrono::duration<double>(clk::now() - t).count(); };
-    if (not m_flush) {
-        if (not m_coder) build_coder();
-        else if (not same_multiplex()) {
-            /* what FrameMultiplexer::process reports (src/FrameMultiplexer.cpp:68-83) */
-            throw FrameMultiplexerError("FrameMultiplexer detected subchannel size change from " +
-                                        std::to_string(m_subs.size()) + " to " +
-                                        std::to_string(m_eti.getSubchannels().size()));
-        }
-        /* the frame's payload at the coder's offsets (the coder reads nothing else of a frame) */
-        uint8_t* frame = m_frames.data() + m_collected * ETI_FRAME;
-        auto fic = m_eti.getFic();
-        fic->process(&m_tmp);
-        memcpy(frame + m_offsets[0], m_tmp.getData(), m_tmp.getLength());
-        for (const auto& md : fic->process_metadata({})) m_meta.push_back(md);
-        size_t i = 1;
-        for (const auto& sub : m_eti.getSubchannels()) {
-            sub->process(&m_tmp);
-            memcpy(frame + m_offsets[i++], m_tmp.getData(), m_tmp.getLength());
-        }
-        m_collected++;
-        m_n_frames++;
-        m_t_collect += since(t0);
+    if (m_flush) {
+        /* end of the stream: first the batch in flight, then (next call) whatever whole TFs are left */
+        m_flush = false;
+        if (m_job.valid()) return collect(dataOut);
+        launch();
+        return collect(dataOut);
     }
+    if (not m_coder) build_coder();
+    else if (not same_multiplex()) {
+        /* what FrameMultiplexer::process reports (src/FrameMultiplexer.cpp:68-83) */
+        throw FrameMultiplexerError("FrameMultiplexer detected subchannel size change from " +
+                                    std::to_string(m_subs.size()) + " to " +
+                                    std::to_string(m_eti.getSubchannels().size()));
+    }
+    /* the frame's payload at the coder's offsets (the coder reads nothing else of a frame) */
+    uint8_t* frame = m_collecting.data() + m_collected * ETI_FRAME;
+    auto fic = m_eti.getFic();
+    fic->process(&m_tmp);
+    memcpy(frame + m_offsets[0], m_tmp.getData(), m_tmp.getLength());
+    for (const auto& md : fic->process_metadata({})) m_meta.push_back(md);
+    size_t i = 1;
+    for (const auto& sub : m_eti.getSubchannels()) {
+        sub->process(&m_tmp);
+        memcpy(frame + m_offsets[i++], m_tmp.getData(), m_tmp.getLength());
+    }
+    m_collected++;
+    m_n_frames++;
+    m_t_collect += std::chrono::duration<double>(clk::now() - t0).count();
 
-    const bool full = m_collected == m_batch * m_cif;
-    if (not full and not m_flush) {
+    if (m_collected < m_batch * m_cif) {
         dataOut->setLength(0);
         return 0;
     }
-    m_flush = false;
-    const size_t n_tf = m_collected / m_cif, n_frames = n_tf * m_cif;
-    if (n_tf == 0) {
-        dataOut->setLength(0);
-        return 0;
-    }
-    const size_t need = n_tf * dabmod_b200_tf_out_bytes(m_chain->handle());
-    const auto t1 = clk::now();
-    pin(dataOut, need);
-    m_t_pin += since(t1);
-    const auto t2 = clk::now();
-    size_t nb = 0;
-    if (dabmod_b200_process_eti_batch(m_chain->handle(), m_coder, m_frames.data(), n_frames, dataOut->getData(),
-                                      dataOut->getLength(), &nb) != DABMOD_B200_OK) {
-        fail("process_eti_batch", dabmod_b200_coder_last_error());
-    }
-    m_t_gpu += since(t2);
-    m_n_batches++;
-    /* frames of an incomplete TF (only after a flush) stay for the next batch */
-    const size_t rest = m_collected - n_frames;
-    if (rest) memmove(m_frames.data(), m_frames.data() + n_frames * ETI_FRAME, rest * ETI_FRAME);
-    m_collected = rest;
-    m_meta_out = std::move(m_meta);
-    m_meta.clear();
-    dataOut->setLength(nb);
-    return (int)nb;
+    /* a batch is complete: take the previous one back (it has had a whole batch of host time), start this one */
+    const int n = collect(dataOut);
+    launch();
+    if (not m_async) return collect(dataOut);           /* ODR_DABMOD_B200_SYNC: no batch in flight between calls */
+    return n;
 }
 
 meta_vec_t B200EtiChain::process_metadata(const meta_vec_t&)

@@ -11,10 +11,14 @@
  *
  * One call per ETI frame, like DabModulator::process.  While a batch fills, process() returns 0 with an empty buffer
  * (the flowgraph iteration ends there, src/Flowgraph.cpp:331-336, as it does on the three of four TM I frames where
- * BlockPartitioner has no block yet); on the call that completes a batch it returns batchTfs transmission frames.
+ * BlockPartitioner has no block yet).  The call that completes batch k starts it on a worker thread and returns
+ * batch k - 1 (batchTfs transmission frames), so the host reads and parses the next frames while the GPU works --
+ * PipelinedModCodec's one-call delay (src/ModPlugin.cpp:90-115) with a batch as the unit; ODR_DABMOD_B200_SYNC in
+ * the environment returns batch k itself.
  * The metadata of every frame of the batch (FicSource::process_metadata, collected like
  * BlockPartitioner::process_metadata does for one TF, src/BlockPartitioner.cpp:126-140) leaves with it.
- * flush() makes the next call emit the whole transmission frames collected so far (end of a file).
+ * flush() makes the next call emit what is pending (end of a file): the batch in flight, then, on a second
+ * flush + call, the whole transmission frames collected so far.
  *
  * A changed multiplex (number, size, position or protection of the subchannels) throws FrameMultiplexerError with
  * the reference's message (src/FrameMultiplexer.cpp:68-83): run_modulator restarts the modulator on it
@@ -27,6 +31,7 @@
 #pragma once
 
 #include <chrono>
+#include <future>
 #include <memory>
 #include <string>
 #include <utility>
@@ -72,8 +77,8 @@ public:
     /* the OFDM chain's controllables ("b200chain" and "tii"): enrol them like B200OfdmChain's */
     B200OfdmChain& chain() { return *m_chain; }
 
-    /* The next process() call emits the whole TFs collected so far and takes no new frame.  Returns false when
-     * there is nothing to emit. */
+    /* The next process() call takes no new frame and emits the batch in flight or, when there is none, the whole
+     * TFs collected so far.  Returns false when there is nothing left to emit. */
     bool flush();
     /* flush() on the live instance, for the end-of-file branch of run_modulator (src/DabMod.cpp:612-617) */
     static bool flush_active();
@@ -81,7 +86,9 @@ public:
 private:
     void build_coder();
     bool same_multiplex() const;
-    void pin(Buffer* dataOut, size_t need);
+    void pin(Buffer& buf, size_t need);
+    void launch();
+    int collect(Buffer* dataOut);
 
     EtiSource& m_eti;
     std::unique_ptr<B200OfdmChain> m_chain;
@@ -97,7 +104,15 @@ private:
     size_t m_cif = 0;               /* ETI frames per TF */
     size_t m_collected = 0;         /* frames in m_frames */
     bool m_flush = false;
-    std::vector<uint8_t> m_frames;  /* m_batch * m_cif frames of 6144 bytes, payload at the coder's offsets */
+    /* m_batch * m_cif frames of 6144 bytes, payload at the coder's offsets: the one being filled, and the two
+     * that batches in flight read from */
+    std::vector<uint8_t> m_collecting, m_frames[2];
+    Buffer m_out[2];                /* where the batches in flight land */
+    int m_next_slot = 0, m_job_slot = 0;
+    std::future<double> m_job;      /* the batch on the GPU (seconds it took) */
+    meta_vec_t m_job_meta;
+    bool m_async = true;
+    double m_t_wait = 0;
     std::vector<int> m_offsets;
     /* what the coder was built for: framesize / startAddress / protection per subchannel */
     struct Sub { size_t framesize, start, protection; };

@@ -106,7 +106,7 @@ def main():
     # end of the input file: the ETI engines still hold the frames of an unfinished batch
     d = edit(d, '                        etiLog.level(info) << "End of file reached.";\n',
              '                        etiLog.level(info) << "End of file reached.";\n'
-             '                        if (B200EtiChain::flush_active()) m.flowgraph->run();\n', "DabMod.cpp")
+             '                        while (B200EtiChain::flush_active()) m.flowgraph->run();\n', "DabMod.cpp")
     save("DabMod.cpp", d)
     print("patch_engine: wrote ConfigParser.cpp DabModulator.cpp DabMod.cpp to", out)
 
