@@ -403,6 +403,9 @@ def measure_binary(n_frames=4000):
         ("reference_binary", ref_bin, "fftw", 0, path, n_frames, "complexf", "/dev/null"),
         ("b200_binary", b200_bin, "b200", 0, path, n_frames, "complexf", "/dev/null"),
         ("b200_binary_depth64", b200_bin, "b200", 64, path, n_frames, "complexf", "/dev/null"),
+        # boundary shape B1: DabModulator.cpp / ConfigParser.cpp / DabMod.cpp unmodified, the hot path's translation
+        # units substituted (adapter/B200Blocks.cpp), the reference's own configuration file
+        ("b1_binary", os.path.join(ROOT, "oracle", "_ref", "odr-dabmod-b1"), "fftw", 0, path, n_frames, "complexf", "/dev/null"),
         ("b200_eti_binary", b200_bin, "b200_eti", 64, path, n_frames, "complexf", "/dev/null"),
         ("b200_eti_binary_long", b200_bin, "b200_eti", 64, long_path, long_n, "complexf", "/dev/null"),
         ("b200_eti_binary_long_s16", b200_bin, "b200_eti", 64, long_path, long_n, "s16", "/dev/null"),
@@ -416,6 +419,9 @@ def measure_binary(n_frames=4000):
             f.write((ini % (src, engine)).replace("format=complexf", "format=" + fmt).replace("filename=/dev/null",
                                                                                              "filename=" + dst))
         env = dict(os.environ, ODR_DABMOD_B200_DEPTH=str(depth), ODR_DABMOD_B200_TRACE="1")
+        if not os.path.exists(binary):
+            res[key] = {"error": "not built"}
+            continue
         try:
             t0 = time.perf_counter()
             r = subprocess.run([binary, cfg], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,

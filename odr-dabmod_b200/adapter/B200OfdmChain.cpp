@@ -9,6 +9,7 @@
 #include <stdexcept>
 #include <vector>
 
+#include "B200Files.h"
 #include "dabmod_b200.h"
 
 namespace {
@@ -16,54 +17,6 @@ namespace {
 [[noreturn]] void fail(const char* what)
 {
     throw std::runtime_error(std::string("B200OfdmChain: ") + what + ": " + dabmod_b200_last_error());
-}
-
-/* FIRFilter::load_filter_taps (src/FIRFilter.cpp:95-141) */
-std::vector<float> load_taps(const std::string& file)
-{
-    std::vector<float> taps;
-    if (file == "default") {
-        taps.resize(dabmod_b200_default_fir_taps(nullptr, 0));
-        dabmod_b200_default_fir_taps(taps.data(), (int)taps.size());
-        return taps;
-    }
-    std::ifstream in(file);
-    if (!in) throw std::runtime_error("FIRFilter: Could not open file with taps! " + file);
-    int n = 0;
-    in >> n;
-    if (n <= 0) throw std::runtime_error("FIRFilter: taps file has invalid format.");
-    taps.resize(n);
-    for (int i = 0; i < n; i++) {
-        in >> taps[i];
-        if (in.fail()) throw std::runtime_error("FIRFilter: file " + file + " should contain more taps");
-    }
-    return taps;
-}
-
-/* MemlessPoly::load_coefficients (src/MemlessPoly.cpp:145-235): returns the
- * dpd_mode and the coefficient block in dabmod_b200_config layout */
-int load_coefs(const std::string& file, std::vector<float>& coefs)
-{
-    std::ifstream in(file);
-    if (!in) throw std::runtime_error("MemlessPoly: Could not open file with coefs!");
-    int fmt = 0;
-    in >> fmt;
-    if (fmt == 1) {
-        int n = 0;
-        in >> n;
-        if (n != 5) throw std::runtime_error("MemlessPoly: invalid number of coefs: " + std::to_string(n));
-        coefs.resize(10);
-        for (auto& c : coefs) in >> c;
-        if (in.fail()) throw std::runtime_error("MemlessPoly: coefs file invalid !");
-        return DABMOD_B200_DPD_ODD_POLY;
-    }
-    if (fmt == 2) {
-        coefs.resize(33);
-        for (auto& c : coefs) in >> c;
-        if (in.fail()) throw std::runtime_error("MemlessPoly: coefs file invalid !");
-        return DABMOD_B200_DPD_LUT;
-    }
-    throw std::runtime_error("MemlessPoly: coef file has unknown format " + std::to_string(fmt));
 }
 
 } // namespace
@@ -100,19 +53,15 @@ B200OfdmChain::B200OfdmChain(mod_settings_t& s, const std::string& format, int d
 
     std::vector<float> taps, coefs;
     if (!s.filterTapsFilename.empty()) {
-        taps = load_taps(s.filterTapsFilename);
+        taps = b200files::load_taps(s.filterTapsFilename);
         c.fir_ntaps = (int32_t)taps.size();
         c.fir_taps = taps.data();
     }
     if (!s.polyCoefFilename.empty()) {
-        c.dpd_mode = load_coefs(s.polyCoefFilename, coefs);
+        c.dpd_mode = b200files::load_coefs(s.polyCoefFilename, coefs);
         c.dpd_coefs = coefs.data();
     }
-    if (format.empty() || format == "complexf") c.format = DABMOD_B200_FMT_COMPLEXF;
-    else if (format == "s16") c.format = DABMOD_B200_FMT_S16;
-    else if (format == "u8") c.format = DABMOD_B200_FMT_U8;
-    else if (format == "s8") c.format = DABMOD_B200_FMT_S8;
-    else throw std::runtime_error("FormatConverter: Invalid format " + format);
+    c.format = b200files::format_code(format);
     c.max_batch = std::max<int32_t>(m_depth > 0 ? (int32_t)m_depth : 1, maxBatch);
 
     if (dabmod_b200_create(&c, &m_handle) != DABMOD_B200_OK) fail("create");

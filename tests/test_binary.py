@@ -194,3 +194,35 @@ def test_eti_engine_in_the_real_binary(tmp_path, case):
     # the batch size changes nothing
     # (gain mode var: per-symbol statistics; the resampler state is carried across batches)
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), case
+
+
+B1_BIN = os.path.join(ROOT, "oracle", "_ref", "odr-dabmod-b1")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (have and os.path.exists(B1_BIN)), reason="oracle/_ref binaries not built (make -C oracle binary b1)")
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_translation_unit_substitution(tmp_path, case):
+    """Boundary shape B1: oracle/_ref/odr-dabmod-b1 is the reference program with DabModulator.cpp,
+    ConfigParser.cpp and DabMod.cpp UNMODIFIED; only the sixteen translation units of the hot path are replaced by
+    adapter/B200Blocks.cpp (same classes, reference headers, the chain on the GPU through the C ABI).  Same
+    configuration file as the reference (fft_engine = fftw | kiss), same remote-control surface, same pipeline
+    delays: the two output files have the same length and agree frame by frame."""
+    mode, n_tf, ref_engine, _, dt, P, kw = CASES[case]
+    if kw.get("poly"):
+        kw = dict(kw, polyfile=str(tmp_path / "poly.coef"))
+        write_poly_file(kw["polyfile"], [1.0, 0.05, -0.02, 0.0, 0.0], [0.0, 0.1, -0.05, 0.0, 0.0])
+    eti_path = make_eti(tmp_path, mode, n_tf)
+    ref = np.fromfile(run_binary(REF_BIN, tmp_path, "ref", eti_path, ref_engine, **kw), dt)
+    got = np.fromfile(run_binary(B1_BIN, tmp_path, "b1", eti_path, ref_engine, **kw), dt)
+    assert got.size == ref.size, (got.size, ref.size)
+    n = n_tf - P
+    a, b = got.reshape(n, -1), ref.reshape(n, -1)
+    for i in range(n):
+        if ref_engine == "kiss":
+            assert np.array_equal(a[i], b[i]), (case, i)
+        elif dt is np.int16:
+            d = np.abs(a[i].astype(np.int32) - b[i].astype(np.int32))
+            assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size, (case, i)
+        else:
+            assert rel_rms(a[i], b[i]) < 2e-6, (case, i)
