@@ -226,3 +226,30 @@ def test_translation_unit_substitution(tmp_path, case):
             assert d.max() <= 1 and np.count_nonzero(d) < 0.01 * d.size, (case, i)
         else:
             assert rel_rms(a[i], b[i]) < 2e-6, (case, i)
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not (have and os.path.exists(B1_BIN)), reason="oracle/_ref binaries not built")
+@pytest.mark.skipif(not _no_gpu(), reason="needs a host without a GPU")
+@pytest.mark.parametrize("binary,engine", [(B1_BIN, "fftw"), (B200_BIN, "b200"), (B200_BIN, "b200_eti")])
+def test_binaries_fail_loudly_without_a_gpu(tmp_path, binary, engine):
+    """CPU: there is no fallback behind any of the three bindings -- the program stops with the library's error
+    instead of computing on the host."""
+    eti_path = make_eti(tmp_path, 1, 4)
+    out = str(tmp_path / "out.iq")
+    ini = str(tmp_path / "cfg.ini")
+    cfg = dict(mode=1, rate=2048000, gainmode="var", digital_gain=1.0, fir=0, poly=0, polyfile="/dev/null", tii=0,
+               fmt="complexf", modulator_extra="")
+    with open(ini, "w") as f:
+        f.write(INI.format(eti=eti_path, engine=engine, out=out, **cfg))
+    r = subprocess.run([binary, ini], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    # (the reference's logger runs on its own thread and does not always get the library's message out before exit)
+    assert r.returncode != 0, r.stdout[-1500:]
+    assert not os.path.exists(out) or os.path.getsize(out) == 0
