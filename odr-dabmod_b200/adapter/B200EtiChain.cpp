@@ -235,11 +235,22 @@ int B200EtiChain::process(Buffer* dataOut)
         return collect(dataOut);
     }
     if (not m_coder) build_coder();
-    else if (not same_multiplex()) {
-        /* what FrameMultiplexer::process reports (src/FrameMultiplexer.cpp:68-83) */
-        throw FrameMultiplexerError("FrameMultiplexer detected subchannel size change from " +
-                                    std::to_string(m_subs.size()) + " to " +
-                                    std::to_string(m_eti.getSubchannels().size()));
+    else if (m_reconfigure or not same_multiplex()) {
+        /* A changed multiplex ends this graph: FrameMultiplexerError, with what FrameMultiplexer::process reports
+         * (src/FrameMultiplexer.cpp:68-83), makes run_modulator build a new modulator (src/DabMod.cpp:744-749).
+         * The frames collected so far are still good: they leave first (one or two calls, whose own frames are
+         * dropped -- the new modulator waits for the next frame with FP 0 anyway, src/DabMod.cpp:691-700). */
+        if (not m_reconfigure) {
+            m_reconfigure = true;
+            m_reconfigure_what = "FrameMultiplexer detected subchannel size change from " + std::to_string(m_subs.size()) +
+                                 " to " + std::to_string(m_eti.getSubchannels().size());
+        }
+        if (m_job.valid()) return collect(dataOut);
+        if (m_collected >= m_cif) {
+            launch();
+            return collect(dataOut);
+        }
+        throw FrameMultiplexerError(m_reconfigure_what);
     }
     /* the frame's payload at the coder's offsets (the coder reads nothing else of a frame) */
     uint8_t* frame = m_collecting.data() + m_collected * ETI_FRAME;

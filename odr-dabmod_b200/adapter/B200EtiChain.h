@@ -20,9 +20,9 @@
  * flush() makes the next call emit what is pending (end of a file): the batch in flight, then, on a second
  * flush + call, the whole transmission frames collected so far.
  *
- * A changed multiplex (number, size, position or protection of the subchannels) throws FrameMultiplexerError with
- * the reference's message (src/FrameMultiplexer.cpp:68-83): run_modulator restarts the modulator on it
- * (src/DabMod.cpp:744-749).
+ * A changed multiplex (number, size, position or protection of the subchannels) first drains the transmission frames
+ * collected so far, then throws FrameMultiplexerError with the reference's message (src/FrameMultiplexer.cpp:68-83):
+ * run_modulator restarts the modulator on it (src/DabMod.cpp:744-749).
  *
  * B200SwapOutput is the OutputMemory of this graph: same role and metadata handling
  * (src/OutputMemory.cpp:62-97), but it exchanges the two buffers' storage instead of copying it -- a batch is
@@ -104,6 +104,8 @@ private:
     size_t m_cif = 0;               /* ETI frames per TF */
     size_t m_collected = 0;         /* frames in m_frames */
     bool m_flush = false;
+    bool m_reconfigure = false;     /* the multiplex has changed: drain, then throw */
+    std::string m_reconfigure_what;
     /* m_batch * m_cif frames of 6144 bytes, payload at the coder's offsets: the one being filled, and the two
      * that batches in flight read from */
     std::vector<uint8_t> m_collecting, m_frames[2];

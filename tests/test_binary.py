@@ -253,3 +253,36 @@ def test_binaries_fail_loudly_without_a_gpu(tmp_path, binary, engine):
     # (the reference's logger runs on its own thread and does not always get the library's message out before exit)
     assert r.returncode != 0, r.stdout[-1500:]
     assert not os.path.exists(out) or os.path.getsize(out) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have, reason="oracle/_ref binaries not built (make -C oracle binary)")
+def test_eti_engine_survives_a_multiplex_reconfiguration(tmp_path):
+    """The ensemble changes in mid-stream (six subchannels -> two).  The reference notices in FrameMultiplexer, restarts
+    the modulator and resumes at the next frame with FP 0 (src/DabMod.cpp:575-579, 691-700, 744-749).  The ETI engine
+    does the same after draining what it has collected: its output is the first part complete, then the second part
+    from the frame the new modulator starts on -- each exactly what a run on that part alone produces."""
+    e = eti_mod()
+    n1, n2 = 40, 64                                         # ETI frames (TM I: 10 and 16 TFs); n1 a multiple of 8
+    part1 = e.synth_eti_range(1, e.default_multiplex(), 0, n1, seed=5)
+    part2 = e.synth_eti_range(1, [(0, 12, e.eep_tpl(0, 1)), (60, 24, e.eep_tpl(0, 3))], n1, n2, seed=6)
+    paths = {}
+    for name, frames in (("both", np.concatenate([part1, part2])), ("p1", part1), ("p2", part2[8:])):
+        paths[name] = str(tmp_path / (name + ".eti"))
+        frames.tofile(paths[name])
+    out = {k: np.fromfile(run_binary(B200_BIN, tmp_path, "eti_" + k, v, "b200_eti", depth=4), np.complex64)
+           for k, v in paths.items()}
+    per_tf = 196608
+    assert out["p1"].size == (n1 // 4) * per_tf and out["p2"].size == ((n2 - 8) // 4) * per_tf
+    assert out["both"].size == out["p1"].size + out["p2"].size
+    assert np.array_equal(out["both"][:out["p1"].size].view(np.uint32), out["p1"].view(np.uint32))
+    assert np.array_equal(out["both"][out["p1"].size:].view(np.uint32), out["p2"].view(np.uint32))
+    # and the reference program on the same file: same frames (it never flushes its one pipelined TF per modulator)
+    ref = np.fromfile(run_binary(REF_BIN, tmp_path, "ref_both", paths["both"], "fftw"), np.complex64)
+    r1 = n1 // 4 - 1
+    assert ref.size == (r1 + (n2 - 8) // 4 - 1) * per_tf
+    for i in range(r1):
+        assert rel_rms(out["both"][i * per_tf:(i + 1) * per_tf], ref[i * per_tf:(i + 1) * per_tf]) < 2e-6, i
+    for i in range((n2 - 8) // 4 - 1):
+        a = out["both"][out["p1"].size + i * per_tf:out["p1"].size + (i + 1) * per_tf]
+        assert rel_rms(a, ref[(r1 + i) * per_tf:(r1 + i + 1) * per_tf]) < 2e-6, i
