@@ -18,9 +18,14 @@
  * the last one, OutputMemory, finds them again through the token and runs the whole chain on the GPU with ONE
  * dabmod_b200_process() call (include/dabmod_b200.h), straight into DabModulator's output buffer.  The output file is
  * therefore aligned like the reference's, including the transmission frames its pipelined blocks never flush.
+ * (A frame runs when its token arrives at OutputMemory: the CFR / PAPR read-outs of "ofdm" cover the frames that have
+ * left the chain, i.e. they trail the reference's by the 1-3 calls of pipeline delay.)
  *
- * What the constructors are given (the pieces of mod_settings_t DabModulator hands to each block, the references
- * included) is collected per graph in a Chain record; the handle is created from it on the first frame.  Remote
+ * The graph describes itself through the same token: QpskSymbolMapper opens a Chain record on its first frame, and
+ * every block the token passes through deposits what its constructor was given (the pieces of mod_settings_t
+ * DabModulator hands to it, the references included; TII, which is not on the token's way, leaves a note in its
+ * output that SignalMultiplexer picks up).  When the first token reaches OutputMemory the record is complete and the
+ * handle is created from it.  Nothing depends on the order in which the blocks were constructed or wired.  Remote
  * control writes go to the referenced settings (so they survive a modulator restart like the reference's) and to
  * the handle.
  *
@@ -92,36 +97,29 @@ struct Chain {
 };
 
 std::mutex g_mtx;
-std::shared_ptr<Chain> g_building;                       /* the graph under construction */
 std::map<uint64_t, std::shared_ptr<Chain>> g_chains;     /* live graphs by id */
-std::map<const void*, std::shared_ptr<Chain>> g_of_block;
+std::map<const void*, std::shared_ptr<Chain>> g_of_block;   /* the graph a block was last seen in */
 uint64_t g_next_id = 1;
 
-/* QpskSymbolMapper is the first block DabModulator constructs (src/DabModulator.cpp:145): it opens a record */
-std::shared_ptr<Chain> open_chain(const void* block)
+/* the first block of the path opens the record of its graph (once per QpskSymbolMapper instance) */
+std::shared_ptr<Chain> chain_of_source(const void* block)
 {
     std::lock_guard<std::mutex> lock(g_mtx);
-    g_building = std::make_shared<Chain>();
-    g_building->id = g_next_id++;
-    g_chains[g_building->id] = g_building;
-    g_of_block[block] = g_building;
-    return g_building;
+    auto it = g_of_block.find(block);
+    if (it != g_of_block.end() && g_chains.count(it->second->id)) return it->second;
+    auto c = std::make_shared<Chain>();
+    c->id = g_next_id++;
+    g_chains[c->id] = c;
+    g_of_block[block] = c;
+    return c;
 }
 
-std::shared_ptr<Chain> join_chain(const void* block)
-{
-    std::lock_guard<std::mutex> lock(g_mtx);
-    if (!g_building) throw std::logic_error("B200Blocks: block constructed outside a DabModulator graph");
-    g_of_block[block] = g_building;
-    return g_building;
-}
-
+/* the graph a block is part of, or nullptr before its first frame */
 std::shared_ptr<Chain> chain_of(const void* block)
 {
     std::lock_guard<std::mutex> lock(g_mtx);
     auto it = g_of_block.find(block);
-    if (it == g_of_block.end()) throw std::logic_error("B200Blocks: unknown block");
-    return it->second;
+    return it == g_of_block.end() || !g_chains.count(it->second->id) ? nullptr : it->second;
 }
 
 std::shared_ptr<Chain> chain_by_id(uint64_t id)
@@ -155,10 +153,35 @@ Token get_token(const Buffer* in, const char* who)
     return t;
 }
 
-void pass(const Buffer* in, Buffer* out, size_t len, const char* who)
+/* Forwards the token and hands `deposit` the graph's record while its handle does not exist yet (the first frames),
+ * so that the block can leave what its constructor was given. */
+template <typename F> void pass(const void* block, const Buffer* in, Buffer* out, size_t len, const char* who, F deposit)
 {
-    put_token(out, len, get_token(in, who));
+    const Token t = get_token(in, who);
+    put_token(out, len, t);
+    auto c = chain_by_id(t.chain);
+    if (!c) return;
+    {
+        std::lock_guard<std::mutex> lock(c->mtx);
+        if (c->handle) return;
+        deposit(*c);
+    }
+    std::lock_guard<std::mutex> lock(g_mtx);
+    g_of_block[block] = c;
 }
+
+void pass(const void* block, const Buffer* in, Buffer* out, size_t len, const char* who)
+{
+    pass(block, in, out, len, who, [](Chain&) {});
+}
+
+/* what TII leaves in its output for SignalMultiplexer */
+constexpr uint64_t TII_MAGIC = 0xb200c0fdb10c0002ull;
+struct TiiNote {
+    uint64_t magic;
+    tii_config_t* conf;
+    const void* block;
+};
 
 [[noreturn]] void not_exported(const std::string& parameter, const std::string& rc_name)
 {
@@ -166,19 +189,21 @@ void pass(const Buffer* in, Buffer* out, size_t len, const char* who)
 }
 
 /* remote control: the handle (when it exists) validates and applies, the caller then stores into the settings */
-void handle_set(Chain& c, const char* name, const std::string& value)
+void handle_set(const std::shared_ptr<Chain>& c, const char* name, const std::string& value)
 {
-    std::lock_guard<std::mutex> lock(c.mtx);
-    if (c.handle && dabmod_b200_set_param(c.handle, name, value.c_str()) != DABMOD_B200_OK) {
+    if (!c) return;                                      /* no frame yet: the settings are all there is */
+    std::lock_guard<std::mutex> lock(c->mtx);
+    if (c->handle && dabmod_b200_set_param(c->handle, name, value.c_str()) != DABMOD_B200_OK) {
         throw ParameterError(dabmod_b200_last_error());
     }
 }
 
-bool handle_get(Chain& c, const char* name, std::string& value)
+bool handle_get(const std::shared_ptr<Chain>& c, const char* name, std::string& value)
 {
-    std::lock_guard<std::mutex> lock(c.mtx);
+    if (!c) return false;
+    std::lock_guard<std::mutex> lock(c->mtx);
     char buf[512];
-    if (!c.handle || dabmod_b200_get_param(c.handle, name, buf, sizeof(buf)) != DABMOD_B200_OK) return false;
+    if (!c->handle || dabmod_b200_get_param(c->handle, name, buf, sizeof(buf)) != DABMOD_B200_OK) return false;
     value = buf;
     return true;
 }
@@ -251,13 +276,11 @@ size_t carriers_of(unsigned mode)
 /* ------------------------------------------------------------------ QpskSymbolMapper (src/QpskSymbolMapper.cpp) */
 QpskSymbolMapper::QpskSymbolMapper(size_t carriers, bool fixedPoint) : ModCodec(), m_fixedPoint(fixedPoint), m_carriers(carriers)
 {
-    auto c = open_chain(this);
-    c->fixed = fixedPoint;
 }
 
 int QpskSymbolMapper::process(Buffer* const dataIn, Buffer* dataOut)
 {
-    auto c = chain_of(this);
+    auto c = chain_of_source(this);
     /* the reference's size rule: whole symbols of carriers * 2 bits */
     if (dataIn->getLength() == 0 || dataIn->getLength() % (m_carriers / 4) != 0) {
         throw std::runtime_error("QpskSymbolMapper::process input size not valid: " + std::to_string(dataIn->getLength()) +
@@ -266,6 +289,10 @@ int QpskSymbolMapper::process(Buffer* const dataIn, Buffer* dataOut)
     Token t{TOKEN_MAGIC, c->id, 0};
     {
         std::lock_guard<std::mutex> lock(c->mtx);
+        if (!c->handle) {
+            c->fixed = m_fixedPoint;
+            c->mode = m_carriers == 1536 ? 1 : m_carriers == 384 ? 2 : m_carriers == 192 ? 3 : m_carriers == 768 ? 4 : 0;
+        }
         t.seq = c->next_seq++;
         const uint8_t* p = reinterpret_cast<const uint8_t*>(dataIn->getData());
         c->frames[t.seq].assign(p, p + dataIn->getLength());
@@ -281,14 +308,13 @@ int QpskSymbolMapper::process(Buffer* const dataIn, Buffer* dataOut)
 FrequencyInterleaver::FrequencyInterleaver(size_t mode, bool fixedPoint) :
     ModCodec(), m_fixedPoint(fixedPoint), m_carriers(carriers_of((unsigned)mode)), m_indices(nullptr)
 {
-    join_chain(this);
 }
 
 FrequencyInterleaver::~FrequencyInterleaver() { forget(this); }
 
 int FrequencyInterleaver::process(Buffer* const dataIn, Buffer* dataOut)
 {
-    pass(dataIn, dataOut, dataIn->getLength(), "FrequencyInterleaver::process");
+    pass(this, dataIn, dataOut, dataIn->getLength(), "FrequencyInterleaver::process");
     return 1;
 }
 
@@ -296,7 +322,6 @@ int FrequencyInterleaver::process(Buffer* const dataIn, Buffer* dataOut)
 PhaseReference::PhaseReference(unsigned int dabmode, bool fixedPoint) :
     ModInput(), d_dabmode(dabmode), d_fixedPoint(fixedPoint), d_carriers(carriers_of(dabmode))
 {
-    join_chain(this)->mode = dabmode;
 }
 
 int PhaseReference::process(Buffer* dataOut)
@@ -309,7 +334,6 @@ int PhaseReference::process(Buffer* dataOut)
 /* --------------------------------------------------------- DifferentialModulator (src/DifferentialModulator.cpp) */
 DifferentialModulator::DifferentialModulator(size_t carriers, bool fixedPoint) : ModMux(), m_carriers(carriers), m_fixedPoint(fixedPoint)
 {
-    join_chain(this);
 }
 
 DifferentialModulator::~DifferentialModulator() { forget(this); }
@@ -318,14 +342,13 @@ DifferentialModulator::~DifferentialModulator() { forget(this); }
 int DifferentialModulator::process(std::vector<Buffer*> dataIn, Buffer* dataOut)
 {
     if (dataIn.size() != 2) throw std::runtime_error("DifferentialModulator::process nb of input streams not 2!");
-    pass(dataIn[1], dataOut, dataIn[0]->getLength() + dataIn[1]->getLength(), "DifferentialModulator::process");
+    pass(this, dataIn[1], dataOut, dataIn[0]->getLength() + dataIn[1]->getLength(), "DifferentialModulator::process");
     return 1;
 }
 
 /* ---------------------------------------------------------------------------------- NullSymbol (src/NullSymbol.cpp) */
 NullSymbol::NullSymbol(size_t numCarriers, size_t typeSize) : ModInput(), m_numCarriers(numCarriers), m_typeSize(typeSize)
 {
-    join_chain(this);
 }
 
 NullSymbol::~NullSymbol() { forget(this); }
@@ -352,7 +375,6 @@ TII::TII(unsigned int dabmode, tii_config_t& tii_config, bool fixedPoint) :
     if (m_conf.pattern < 0 || m_conf.pattern > 69) throw TIIError("TII::TII pattern not valid!");
     if (m_conf.comb < 0 || m_conf.comb > 23) throw TIIError("TII::TII comb not valid!");
     m_carriers = carriers_of(dabmode);
-    join_chain(this)->tii = &tii_config;
 }
 
 const char* TII::name()
@@ -367,6 +389,9 @@ int TII::process(Buffer* dataIn, Buffer* dataOut)
 {
     if (dataIn == nullptr || dataOut == nullptr) throw TIIError("TII::process received a NULL buffer");
     dataOut->setLength(m_carriers * (m_fixedPoint ? sizeof(complexfix) : sizeof(complexf)));
+    /* TII is not on the token's way (its input is a phase reference): SignalMultiplexer picks this note up */
+    const TiiNote note{TII_MAGIC, &m_conf, this};
+    memcpy(dataOut->getData(), &note, sizeof(note));
     return 1;
 }
 
@@ -378,24 +403,24 @@ void TII::set_parameter(const std::string& parameter, const std::string& value)
     auto c = chain_of(this);
     if (parameter == "enable") {
         const int v = parse<int>(value);
-        handle_set(*c, "tii.enable", value);
+        handle_set(c, "tii.enable", value);
         m_conf.enable = v != 0;
     }
     else if (parameter == "pattern") {
         const int v = parse<int>(value);
         if (v < 0 || v > 69) throw ParameterError("TII pattern not valid!");
-        handle_set(*c, "tii.pattern", value);
+        handle_set(c, "tii.pattern", value);
         m_conf.pattern = v;
     }
     else if (parameter == "comb") {
         const int v = parse<int>(value);
         if (v < 0 || v > 23) throw ParameterError("TII comb not valid!");
-        handle_set(*c, "tii.comb", value);
+        handle_set(c, "tii.comb", value);
         m_conf.comb = v;
     }
     else if (parameter == "old_variant") {
         const int v = parse<int>(value);
-        handle_set(*c, "tii.old_variant", value);
+        handle_set(c, "tii.old_variant", value);
         m_conf.old_variant = v != 0;
     }
     else not_exported(parameter, get_rc_name());
@@ -428,23 +453,38 @@ int SignalMultiplexer::process(std::vector<Buffer*> dataIn, Buffer* dataOut)
 {
     if (dataIn.size() != 2 && dataIn.size() != 3) throw std::runtime_error("SignalMultiplexer::process needs 2 or 3 inputs");
     const size_t null_len = dataIn[dataIn.size() == 3 ? 2 : 0]->getLength();
-    pass(dataIn[1], dataOut, null_len + dataIn[1]->getLength(), "SignalMultiplexer::process");
+    const Buffer* tii = dataIn.size() == 3 ? dataIn[2] : nullptr;
+    const void* tii_block = nullptr;
+    pass(this, dataIn[1], dataOut, null_len + dataIn[1]->getLength(), "SignalMultiplexer::process", [&](Chain& c) {
+        TiiNote note{};
+        if (tii && tii->getData() && tii->getLength() >= sizeof(note)) memcpy(&note, tii->getData(), sizeof(note));
+        if (note.magic == TII_MAGIC) {
+            c.tii = note.conf;
+            tii_block = note.block;
+        }
+    });
+    if (tii_block) {
+        auto c = chain_of(this);
+        std::lock_guard<std::mutex> lock(g_mtx);
+        if (c) g_of_block[tii_block] = c;
+    }
     return 1;
 }
 
 /* ---------------------------------------------------------------------------- CicEqualizer (src/CicEqualizer.cpp) */
-CicEqualizer::CicEqualizer(size_t nbCarriers, size_t spacing, int R) : ModCodec(), myNbCarriers(nbCarriers), mySpacing(spacing)
+CicEqualizer::CicEqualizer(size_t nbCarriers, size_t spacing, int R) :
+    ModCodec(), myNbCarriers(nbCarriers), mySpacing(spacing), myFilter(1, (float)std::max(R, 1))   /* the ratio, kept */
 {
-    auto c = join_chain(this);
-    c->cic = true;
-    c->cic_ratio = (size_t)std::max(R, 1);
 }
 
 CicEqualizer::~CicEqualizer() { forget(this); }
 
 int CicEqualizer::process(Buffer* const dataIn, Buffer* dataOut)
 {
-    pass(dataIn, dataOut, dataIn->getLength(), "CicEqualizer::process");
+    pass(this, dataIn, dataOut, dataIn->getLength(), "CicEqualizer::process", [&](Chain& c) {
+        c.cic = true;
+        c.cic_ratio = (size_t)myFilter[0];
+    });
     return 1;
 }
 
@@ -465,10 +505,6 @@ OfdmGeneratorCF32::OfdmGeneratorCF32(size_t nbSymbols, size_t nbCarriers, size_t
     RC_ADD_PARAMETER(errorclip, "CFR: Limit error");
     RC_ADD_PARAMETER(clip_stats, "CFR: statistics (clip ratio, errorclip ratio)");
     RC_ADD_PARAMETER(papr, "PAPR measurements (before CFR, after CFR)");
-    auto c = join_chain(this);
-    c->cfr = &enableCfr;
-    c->cfr_clip = &cfrClip;
-    c->cfr_errclip = &cfrErrorClip;
 }
 
 OfdmGeneratorCF32::~OfdmGeneratorCF32() { forget(this); }
@@ -479,7 +515,11 @@ int OfdmGeneratorCF32::process(Buffer* const dataIn, Buffer* dataOut)
         throw std::runtime_error("OfdmGenerator::process input size not valid! IN " + std::to_string(dataIn->getLength()) +
                                  " != " + std::to_string(myNbSymbols * myNbCarriers * sizeof(complexf)));
     }
-    pass(dataIn, dataOut, myNbSymbols * mySpacing * sizeof(complexf), "OfdmGenerator::process");
+    pass(this, dataIn, dataOut, myNbSymbols * mySpacing * sizeof(complexf), "OfdmGenerator::process", [&](Chain& c) {
+        c.cfr = &myCfr;
+        c.cfr_clip = &myCfrClip;
+        c.cfr_errclip = &myCfrErrorClip;
+    });
     return 1;
 }
 
@@ -490,19 +530,19 @@ void OfdmGeneratorCF32::set_parameter(const std::string& parameter, const std::s
     auto c = chain_of(this);
     if (parameter == "cfr") {
         const int v = parse<int>(value);
-        handle_set(*c, "cfr", value);
+        handle_set(c, "cfr", value);
         std::lock_guard<std::mutex> lock(myCfrRcMutex);
         myCfr = v != 0;
     }
     else if (parameter == "clip") {
         const float v = parse<float>(value);
-        handle_set(*c, "clip", value);
+        handle_set(c, "clip", value);
         std::lock_guard<std::mutex> lock(myCfrRcMutex);
         myCfrClip = v;
     }
     else if (parameter == "errorclip") {
         const float v = parse<float>(value);
-        handle_set(*c, "errorclip", value);
+        handle_set(c, "errorclip", value);
         std::lock_guard<std::mutex> lock(myCfrRcMutex);
         myCfrErrorClip = v;
     }
@@ -522,7 +562,7 @@ const std::string OfdmGeneratorCF32::get_parameter(const std::string& parameter)
     else if (parameter == "clip_stats" || parameter == "papr") {
         /* the device-side per-symbol records, aggregated into the reference's strings by the library */
         auto c = chain_of(this);
-        if (handle_get(*c, parameter.c_str(), v)) ss << v;
+        if (handle_get(c, parameter.c_str(), v)) ss << v;
         else ss << (parameter == "papr" ? "0 0" : "No stats available");
     }
     else not_exported(parameter, get_rc_name());
@@ -541,7 +581,6 @@ OfdmGeneratorFixed::OfdmGeneratorFixed(size_t nbSymbols, size_t nbCarriers, size
 {
     if (!inverse) throw std::runtime_error("OfdmGenerator: only the inverse transform of the modulator is accelerated");
     if (nbCarriers > spacing) throw std::runtime_error("OfdmGenerator nbCarriers > spacing!");
-    join_chain(this)->fixed = true;
 }
 
 OfdmGeneratorFixed::~OfdmGeneratorFixed() { forget(this); }
@@ -551,7 +590,7 @@ int OfdmGeneratorFixed::process(Buffer* const dataIn, Buffer* dataOut)
     if (dataIn->getLength() != myNbSymbols * myNbCarriers * sizeof(complexfix)) {
         throw std::runtime_error("OfdmGenerator::process input size not valid!");
     }
-    pass(dataIn, dataOut, myNbSymbols * mySpacing * sizeof(complexfix), "OfdmGenerator::process");
+    pass(this, dataIn, dataOut, myNbSymbols * mySpacing * sizeof(complexfix), "OfdmGenerator::process", [](Chain& c) { c.fixed = true; });
     return 1;
 }
 
@@ -563,11 +602,6 @@ GainControl::GainControl(size_t framesize, GainMode& gainMode, float& digGain, f
     RC_ADD_PARAMETER(digital, "Digital Gain");
     RC_ADD_PARAMETER(mode, "Gainmode (fix|max|var)");
     RC_ADD_PARAMETER(var, "Variance setting for gainmode var (default: 4)");
-    auto c = join_chain(this);
-    c->gain_mode = &gainMode;
-    c->digital = &digGain;
-    c->variance = &varVariance;
-    c->normalise = normalise;
     start_pipeline_thread();
 }
 
@@ -579,7 +613,12 @@ GainControl::~GainControl()
 
 int GainControl::internal_process(Buffer* const dataIn, Buffer* dataOut)
 {
-    pass(dataIn, dataOut, dataIn->getLength(), "GainControl::internal_process");
+    pass(this, dataIn, dataOut, dataIn->getLength(), "GainControl::internal_process", [&](Chain& c) {
+        c.gain_mode = &m_gainmode;
+        c.digital = &m_digGain;
+        c.variance = &m_var_variance_rc;
+        c.normalise = m_normalise;
+    });
     return 1;
 }
 
@@ -588,20 +627,20 @@ void GainControl::set_parameter(const std::string& parameter, const std::string&
     auto c = chain_of(this);
     if (parameter == "digital") {
         const float v = parse<float>(value);
-        handle_set(*c, "digital", value);
+        handle_set(c, "digital", value);
         m_digGain = v;
     }
     else if (parameter == "mode") {
         std::string m = parse<std::string>(value);
         std::transform(m.begin(), m.end(), m.begin(), [](char ch) { return (char)std::tolower(ch); });
         if (m != "fix" && m != "max" && m != "var") throw ParameterError("Gainmode " + m + " unknown");
-        handle_set(*c, "mode", m);
+        handle_set(c, "mode", m);
         std::lock_guard<std::mutex> lock(m_mutex);
         m_gainmode = m == "fix" ? GainMode::GAIN_FIX : m == "max" ? GainMode::GAIN_MAX : GainMode::GAIN_VAR;
     }
     else if (parameter == "var") {
         const float v = parse<float>(value);
-        handle_set(*c, "var", value);
+        handle_set(c, "var", value);
         std::lock_guard<std::mutex> lock(m_mutex);
         m_var_variance_rc = v;
     }
@@ -640,7 +679,6 @@ GuardIntervalInserter::GuardIntervalInserter(size_t nbSymbols, size_t spacing, s
     RC_ADD_PARAMETER(windowlen, "Window length for OFDM windowng [0 to disable]");
     /* the reference's rule (update_window): the window may not exceed the guard interval */
     update_window(windowOverlap);
-    join_chain(this)->window = &windowOverlap;
 }
 
 void GuardIntervalInserter::update_window(size_t new_window_overlap)
@@ -658,8 +696,8 @@ int GuardIntervalInserter::process(Buffer* const dataIn, Buffer* dataOut)
     if (dataIn->getLength() != (m_params.nbSymbols + 1) * m_params.spacing * sample) {
         throw std::runtime_error("GuardIntervalInserter::process error on input size");
     }
-    pass(dataIn, dataOut, (m_params.nullSize + m_params.nbSymbols * m_params.symSize) * sample,
-         "GuardIntervalInserter::process");
+    pass(this, dataIn, dataOut, (m_params.nullSize + m_params.nbSymbols * m_params.symSize) * sample,
+         "GuardIntervalInserter::process", [&](Chain& c) { c.window = &m_params.windowOverlap; });
     return 1;
 }
 
@@ -670,7 +708,7 @@ void GuardIntervalInserter::set_parameter(const std::string& parameter, const st
         const size_t old = m_params.windowOverlap;
         try { update_window(v); }
         catch (const std::out_of_range& e) { throw ParameterError(e.what()); }
-        try { handle_set(*chain_of(this), "windowlen", value); }
+        try { handle_set(chain_of(this), "windowlen", value); }
         catch (...) { update_window(old); throw; }
     }
     else not_exported(parameter, get_rc_name());
@@ -696,7 +734,6 @@ FIRFilter::FIRFilter(std::string& taps_file) : PipelinedModCodec(), RemoteContro
 {
     RC_ADD_PARAMETER(ntaps, "(Read-only) number of filter taps.");
     RC_ADD_PARAMETER(tapsfile, "Filename containing filter taps. When written to, the new file gets automatically loaded.");
-    join_chain(this);
     load_filter_taps(m_taps_file);
     start_pipeline_thread();
 }
@@ -710,8 +747,7 @@ FIRFilter::~FIRFilter()
 void FIRFilter::load_filter_taps(const std::string& tapsFile)
 {
     std::vector<float> taps = b200files::load_taps(tapsFile);
-    auto c = chain_of(this);
-    {
+    if (auto c = chain_of(this)) {
         std::lock_guard<std::mutex> lock(c->mtx);
         if (c->handle) {
             std::stringstream ss;
@@ -730,7 +766,10 @@ void FIRFilter::load_filter_taps(const std::string& tapsFile)
 
 int FIRFilter::internal_process(Buffer* const dataIn, Buffer* dataOut)
 {
-    pass(dataIn, dataOut, dataIn->getLength(), "FIRFilter::internal_process");
+    pass(this, dataIn, dataOut, dataIn->getLength(), "FIRFilter::internal_process", [&](Chain& c) {
+        std::lock_guard<std::mutex> lock(m_taps_mutex);
+        c.taps = m_taps;
+    });
     return 1;
 }
 
@@ -783,14 +822,13 @@ Resampler::Resampler(size_t inputRate, size_t outputRate, size_t resolution) :
     L = outputRate / a;
     M = inputRate / a;
     if (inputRate != 2048000) throw std::runtime_error("Resampler: the modulator resamples from 2 048 000 samples/s");
-    join_chain(this)->out_rate = outputRate;
 }
 
 Resampler::~Resampler() { forget(this); }
 
 int Resampler::process(Buffer* const dataIn, Buffer* dataOut)
 {
-    pass(dataIn, dataOut, dataIn->getLength() * L / M, "Resampler::process");
+    pass(this, dataIn, dataOut, dataIn->getLength() * L / M, "Resampler::process", [&](Chain& c) { c.out_rate = 2048000 / M * L; });
     return 1;
 }
 
@@ -801,7 +839,6 @@ MemlessPoly::MemlessPoly(std::string& coefs_file, unsigned int) :
     RC_ADD_PARAMETER(ncoefs, "(Read-only) number of coefficients.");
     RC_ADD_PARAMETER(coefs, "Predistortion coefficients, same format as file.");
     RC_ADD_PARAMETER(coeffile, "Filename containing coefficients. When set, the file gets loaded.");
-    join_chain(this);
     std::ifstream in(coefs_file);
     if (!in) throw std::runtime_error("MemlessPoly: Could not open file with coefs!");
     load_coefficients(in);
@@ -823,8 +860,7 @@ void MemlessPoly::load_coefficients(std::istream& coefData)
     std::vector<float> coefs;
     std::istringstream parse_in(text.str());
     const int mode = b200files::load_coefs(parse_in, coefs);
-    auto c = chain_of(this);
-    {
+    if (auto c = chain_of(this)) {
         std::lock_guard<std::mutex> lock(c->mtx);
         if (c->handle && dabmod_b200_set_param(c->handle, "coefs", text.str().c_str()) != DABMOD_B200_OK) {
             throw std::runtime_error(dabmod_b200_last_error());
@@ -865,7 +901,19 @@ std::string MemlessPoly::serialise_coefficients() const
 
 int MemlessPoly::internal_process(Buffer* const dataIn, Buffer* dataOut)
 {
-    pass(dataIn, dataOut, dataIn->getLength(), "MemlessPoly::internal_process");
+    pass(this, dataIn, dataOut, dataIn->getLength(), "MemlessPoly::internal_process", [&](Chain& c) {
+        std::lock_guard<std::mutex> lock(m_coefs_mutex);
+        c.dpd_mode = m_dpd_type == dpd_type_t::lookup_table ? DABMOD_B200_DPD_LUT : DABMOD_B200_DPD_ODD_POLY;
+        c.coefs.clear();
+        if (m_dpd_type == dpd_type_t::lookup_table) {
+            c.coefs.push_back(m_lut_scalefactor);
+            for (const auto& l : m_lut) c.coefs.push_back(l.real());
+        }
+        else {
+            c.coefs.insert(c.coefs.end(), m_coefs_am.begin(), m_coefs_am.end());
+            c.coefs.insert(c.coefs.end(), m_coefs_pm.begin(), m_coefs_pm.end());
+        }
+    });
     return 1;
 }
 
@@ -918,7 +966,6 @@ FormatConverter::FormatConverter(bool input_is_complexfix_wide, const std::strin
 {
     if (input_is_complexfix_wide) throw std::runtime_error("FormatConverter: the DEXTER sample format is not accelerated");
     get_format_size(format_out);                          /* throws on an unknown format */
-    join_chain(this)->format = format_out;
 }
 
 FormatConverter::~FormatConverter()
@@ -931,11 +978,13 @@ int FormatConverter::process(Buffer* const dataIn, Buffer* dataOut)
 {
     /* float components in, one converted component each out */
     const size_t components = dataIn->getLength() / sizeof(float);
-    pass(dataIn, dataOut, components * (get_format_size(m_format_out) / 2), "FormatConverter::process");
+    pass(this, dataIn, dataOut, components * (get_format_size(m_format_out) / 2), "FormatConverter::process",
+         [&](Chain& c) { c.format = m_format_out; });
     /* the count of the frame the GPU converted last (the reference reports the last frame it converted) */
-    auto c = chain_of(this);
-    std::lock_guard<std::mutex> lock(c->mtx);
-    if (c->handle) m_num_clipped_samples.store(dabmod_b200_num_clipped_samples(c->handle));
+    if (auto c = chain_of(this)) {
+        std::lock_guard<std::mutex> lock(c->mtx);
+        if (c->handle) m_num_clipped_samples.store(dabmod_b200_num_clipped_samples(c->handle));
+    }
     return 1;
 }
 
@@ -953,14 +1002,11 @@ size_t FormatConverter::get_format_size(const std::string& format)
 /* ------------------------------------------------------------------------------ OutputMemory (src/OutputMemory.cpp) */
 OutputMemory::OutputMemory(Buffer* dataOut) : ModOutput(), m_dataOut(dataOut)
 {
-    /* the last block DabModulator constructs (src/DabModulator.cpp:279): the record is complete */
-    join_chain(this);
-    std::lock_guard<std::mutex> lock(g_mtx);
-    g_building.reset();
 }
 
 OutputMemory::~OutputMemory()
 {
+    /* the graph ends with its sink: the record, the handle and every block's entry go with it */
     std::shared_ptr<Chain> c;
     {
         std::lock_guard<std::mutex> lock(g_mtx);
@@ -968,7 +1014,6 @@ OutputMemory::~OutputMemory()
         if (it != g_of_block.end()) {
             c = it->second;
             g_chains.erase(c->id);
-            /* every block of this graph goes with it */
             for (auto b = g_of_block.begin(); b != g_of_block.end();) {
                 if (b->second == c) b = g_of_block.erase(b);
                 else ++b;
@@ -982,6 +1027,10 @@ int OutputMemory::process(Buffer* dataIn)
     const Token t = get_token(dataIn, "OutputMemory::process");
     auto c = chain_by_id(t.chain);
     if (!c) throw std::runtime_error("OutputMemory::process: frame of a graph that no longer exists");
+    {
+        std::lock_guard<std::mutex> lock(g_mtx);
+        g_of_block[this] = c;
+    }
     std::lock_guard<std::mutex> lock(c->mtx);
     auto it = c->frames.find(t.seq);
     if (it == c->frames.end()) throw std::runtime_error("OutputMemory::process: transmission frame lost on the way");

@@ -14,6 +14,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(HERE, "_ref", "libdabmod_ref.so")
 REF_LIB_FAST = os.path.join(HERE, "_ref", "fast", "libdabmod_ref.so")     # the same sources with -ffast-math
+# the same harness linked with the product's adapter/B200Blocks.cpp in place of the sixteen hot-path translation units
+# (boundary shape B1): needs a GPU, used by tests/test_b1_blocks.py as the thing under test, never as a checker
+B1_LIB = os.path.join(HERE, "_ref", "libdabmod_b1.so")
 
 TF_BYTES = {1: 75 * 384, 2: 75 * 96, 3: 152 * 48, 4: 75 * 192}
 TF_SAMPLES = {1: 196608, 2: 49152, 3: 49152, 4: 98304}
@@ -46,7 +49,7 @@ class _RefCfg(ctypes.Structure):
 
 
 def available(variant=None):
-    return os.path.exists(REF_LIB_FAST if variant == "fast" else REF_LIB)
+    return os.path.exists({"fast": REF_LIB_FAST, "b1": B1_LIB}.get(variant, REF_LIB))
 
 
 _lib = None
@@ -55,14 +58,14 @@ _libs = {}
 
 def lib(variant=None):
     global _lib
-    if variant == "fast":
-        if "fast" not in _libs:
+    if variant in ("fast", "b1"):
+        if variant not in _libs:
             saved, _lib = _lib, None
             try:
-                _libs["fast"] = _load(REF_LIB_FAST)
+                _libs[variant] = _load(REF_LIB_FAST if variant == "fast" else B1_LIB)
             finally:
                 _lib = saved
-        return _libs["fast"]
+        return _libs[variant]
     if _lib is None:
         _lib = _load(REF_LIB)
     return _lib
