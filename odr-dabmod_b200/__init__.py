@@ -15,7 +15,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libdabmod_b200.so")
+# DABMOD_B200_LIB: an experimental build of the same library (tools/*_exp.sh)
+LIB_PATH = os.environ.get("DABMOD_B200_LIB") or os.path.join(HERE, "libdabmod_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 ABI_VERSION = 2

@@ -27,7 +27,10 @@ namespace dabmod {
 
 constexpr int SW_WARPS = 12;                // warps (= symbols in flight) per CTA
 constexpr int SW_THREADS = SW_WARPS * 32;
-constexpr int SW_GROUPS = 1;                // 1: all warps in step; 2: two groups half a symbol apart (measured slower)
+#ifndef SW_GROUPS_N
+#define SW_GROUPS_N 2
+#endif
+constexpr int SW_GROUPS = SW_GROUPS_N;      // 1: all warps in step; 2 / 4: groups of warps on the same sub-partitions, staggered
 constexpr int SW_XPAD = 65;                 // lane stride (complex) of the exchange buffer
 constexpr int SW_N = 2048, SW_K = 1536;
 constexpr int SW_CPL = SW_K / 32;           // 48 source carriers per lane
@@ -162,9 +165,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     // different places in it would each stream it separately (measured: 1.03 ms free-running,
     // 0.62 ms in step).  SW_GROUPS == 2 splits them into two groups half a symbol apart so
     // that one group's store/scatter latency overlaps the other's butterflies; the second
-    // instruction stream costs more than the overlap gains (0.65 ms).
+    // instruction stream costs more than the overlap gains (0.65 ms) -- when the groups are warps 0-5 and 6-11, which
+    // puts both streams on every sub-partition.  With the groups on DISJOINT sub-partitions (a warp's scheduler is
+    // warp % 4: group = bit 1 of the warp index) each sub-partition's instruction cache follows one stream and the
+    // overlap pays: 0.461 -> 0.430 ms per 1024 TFs (four groups, one per sub-partition: 0.440 ms).
     constexpr int GRP_THREADS = SW_THREADS / SW_GROUPS;
-    const int grp = warp / (SW_WARPS / SW_GROUPS);
+    // a warp's scheduler (SM sub-partition) is warp % 4: a group keeps to its own sub-partitions, so that each
+    // sub-partition's instruction cache follows ONE instruction stream
+    const int grp = SW_GROUPS == 4 ? (warp & 3) : SW_GROUPS == 2 ? ((warp >> 1) & 1) : 0;
     bool first_iter = true;
 
     // Work split: the batch is one sequence of n_tf * L transformed symbols (symbol s = 1..L of
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     {
         for (int it = 0; it < per_warp; it++) {
             sw_bar_sync(1 + grp, GRP_THREADS);
-            if (SW_GROUPS == 2 && first_iter && grp == 1) sw_bar_sync(3, SW_THREADS);     // wait for group 0's half-way mark
+            if (SW_GROUPS > 1 && first_iter && grp > 0) __nanosleep(2500u * 4u / SW_GROUPS * grp);   // start the groups apart
             const long long g = g0 + it;
             const bool fft_symbol = g < g1;
             const int tf = fft_symbol ? (int)(g / L) : 0;
@@ -286,7 +294,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                 for (int r = 0; r < 64; r++) xb[lane * SW_XPAD + r] = v[r];
                 __syncwarp();
             }
-            if (SW_GROUPS == 2 && first_iter && grp == 0) sw_bar_arrive(3, SW_THREADS);   // half-way mark of the first symbol
             first_iter = false;
             if (fft_symbol) {
                 // ---- pass 2: butterflies j = lane and lane + 32 (radix 32), sample n = j + 64 r ----
