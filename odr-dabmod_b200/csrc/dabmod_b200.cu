@@ -237,7 +237,6 @@ struct dabmod_b200 {
     bool res_q = false;            // k_resample_q applies (Ni = 4096, No = P * 4000, P = 2..5)
     bool allow_res_up = true;      // "res_kernel" knob: 0 = always the generic kernel
     int res_kernel = 1;            //   2 = the older variant of a fast kernel where two exist
-    bool fuse_proto = false;       // "fuse_proto": timing prototype of the fused symbol + FIR kernel (wrong seams)
     int res_dbg = 0;               // "res_dbg": profiling aid, skips parts of the resampler kernels (wrong results)
     size_t res_smem = 0;
 
@@ -593,8 +592,10 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         // persistent: one CTA per SM, every warp takes one contiguous range of the batch's symbols
         const long long n_sym = (long long)n_tf * m.L;
         const int wgrid = (int)std::min<long long>((n_sym + SW_WARPS - 1) / SW_WARPS, h->sm_count);
-        ProfScope prof_w(h, h->fuse_proto ? "k_symbols_w_fuse" : "k_symbols_w", s);
-        if (h->fuse_proto && !sym_post) {
+        // "fir_kernel" = 3: the 45-tap FIR inside the symbol kernel (complexf out of the FIR stage; symbols_warp.cuh FUSE)
+        const bool fused = compact && !post && h->fir_kernel >= 3;
+        ProfScope prof_w(h, fused ? "k_symbols_w_fir" : "k_symbols_w", s);
+        if (fused) {
             for (size_t j = 0; j < 45 && j < h->fir_taps.size(); j++) wp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
             wp.compact = 0;
             wp.s.out = dst;
@@ -1557,7 +1558,6 @@ int dabmod_b200_set_param(dabmod_b200 *h, const char *name, const char *value)
             else if (n == "fir_kernel") { int v; ss >> v; h->use_fir_sym = v != 0; h->fir_kernel = v; }
             else if (n == "res_kernel") { int v; ss >> v; h->allow_res_up = v != 0; h->res_kernel = v; }
             else if (n == "res_dbg") { int v; ss >> v; h->res_dbg = v; }
-            else if (n == "fuse_proto") { int v; ss >> v; h->fuse_proto = v != 0; }
             else if (n == "var") { ss >> c.gain_variance; }
             else if (n == "mode") {
                 std::string v; ss >> v;

@@ -56,7 +56,7 @@ struct SymWParams {
     SymParams s;                            // shared with k_symbols
     const float2 *twiddle_w;                // 31 * 64 entries
     int n_tf;
-    float2 taps[45];                        // FUSE: the default FIR taps as (tap, tap) pairs
+    float2 taps[45];                        // FUSE: the FIR taps as (tap, tap) pairs
     int compact;                            // 1: write only the N samples of every data symbol, back to back
                                             // ([tf][s-1][N], no null symbol, no cyclic prefix): the layout
                                             // k_fir_sym reads (it rebuilds the guard interval itself)
@@ -222,12 +222,21 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
         // bit row of the first data symbol of the range; afterwards always one symbol ahead
         if (s_first >= 2) nextrow = sw_fetch_row(bits + (size_t)(s_first - 2) * (K / 4), lane);
     }
+    // FUSE: the 45-tap FIR (FIRFilter.cpp:168-191: out[n] = sum_j taps[j] in[n + j]) runs on the staged symbol before
+    // it leaves.  The last 44 outputs of a symbol's body reach into the next symbol's cyclic prefix: they are
+    // computed one iteration later, from the 44 samples carried in registers and the prefix head of the symbol then
+    // staged.  A warp whose range ends inside a transmission frame therefore assembles ONE symbol more (the first of
+    // its neighbour's range, "ghost": nothing of it is stored) to finish its own last symbol.
+    float2 carry0 = make_float2(0.f, 0.f), carry1 = carry0;     // lane < 22: samples 2004 + 2 lane (+ 1) of the previous symbol
+    bool have_carry = false;
+    const bool need_ghost = FUSE && g1 > g0 && g1 < n_sym && (g1 % L) != 0;
     {
-        for (int it = 0; it < per_warp; it++) {
+        for (int it = 0; it < per_warp + (FUSE ? 1 : 0); it++) {
             sw_bar_sync(1 + grp, GRP_THREADS);
             if (SW_GROUPS > 1 && first_iter && grp > 0) __nanosleep(2500u * 4u / SW_GROUPS * grp);   // start the groups apart
             const long long g = g0 + it;
-            const bool fft_symbol = g < g1;
+            const bool ghost = FUSE && need_ghost && g == g1;
+            const bool fft_symbol = g < g1 || ghost;
             const int tf = fft_symbol ? (int)(g / L) : 0;
             const int s = 1 + (int)(g - (long long)tf * L);
             const uint8_t *bits = p.bits + (size_t)tf * p.tf_in_bytes;
@@ -237,8 +246,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                 // whatever gain it borrows from symbol 1 (GainControl.cpp:139-144).  The
                 // differential chain restarts from the phase reference (DifferentialModulator.cpp:65).
                 if (!pw.compact) {
-                    for (int i = lane; i < p.null_size; i += 32)
+                    // (FUSE: the last 44 samples of the filtered null symbol see the first prefix, see below)
+                    for (int i = lane; i < p.null_size - (FUSE ? 44 : 0); i += 32)
                         store_sample<POST>(p.out, out_base + i, make_float2(0.f, 0.f), p.post, clip);
+                }
+                if (FUSE) {
+                    carry0 = carry1 = make_float2(0.f, 0.f);        // the null symbol ends in zeros
+                    have_carry = true;
                 }
 #pragma unroll
                 for (int w = 0; w < 6; w++) ph[w] = sm.ph0[w * 32 + lane];
@@ -246,7 +260,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
             if (fft_symbol) {
                 // ---- 1. differential phase of this symbol, scattered by FFT bin as byte codes ----
                 const RowBits b = sw_unpack_row(nextrow, lane);
-                if (s + 1 <= L && g + 1 < g1) nextrow = sw_fetch_row(bits + (size_t)(s - 1) * (K / 4), lane);
+                if (s + 1 <= L && (g + 1 < g1 || (need_ghost && g + 1 == g1)))
+                    nextrow = sw_fetch_row(bits + (size_t)(s - 1) * (K / 4), lane);
                 if (s >= 2) {
 #pragma unroll
                     for (int w = 0; w < 6; w++) {
@@ -384,18 +399,51 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 64; i++) xb[lane + 32 * i] = cscale(y[i], g_sym);
                     if (FUSE) {
-                        // PROTOTYPE (timing only, seams not wired): the 45-tap filter in place over the staged symbol,
-                        // a lane owning 17 consecutive outputs per pass (odd lane stride: conflict free)
                         __syncwarp();
+                        float2 *const outp = reinterpret_cast<float2 *>(p.out);
+                        // The phase codes are dead until the next symbol: their buffer holds the seam windows.
+                        //   strip A = prefix end ++ body start = samples 2004..2047 ++ 0..43 of this symbol
+                        //             -> the 44 outputs across the prefix/body seam, prefix positions 460..503
+                        //   strip B = the previous symbol's samples 2004..2047 (carried; zeros after the null symbol)
+                        //             ++ this symbol's prefix head = its samples 1544..1587
+                        //             -> the last 44 body outputs of the previous symbol, resp. the end of the null symbol
+                        float2 *const strip = reinterpret_cast<float2 *>(code);
+                        if (!ghost) {
+                            for (int i = lane; i < 88; i += 32) strip[i] = i < 44 ? xb[2004 + i] : xb[i - 44];
+                        }
+                        if (have_carry) {
+                            if (lane < 22) { strip[88 + 2 * lane] = carry0; strip[88 + 2 * lane + 1] = carry1; }
+                            for (int i = lane; i < 44; i += 32) strip[132 + i] = xb[1544 + i];
+                        }
+                        const bool tf_end = s == L && !ghost;
+                        const int cl = lane < 22 ? lane : 21;
+                        const float2 nc0 = xb[2004 + 2 * cl], nc1 = xb[2005 + 2 * cl];
+                        __syncwarp();
+                        // The body outputs whose window stays inside the symbol, 0..2003, are filtered in place: a lane
+                        // owns 17 consecutive outputs per pass (odd lane stride: conflict free); everybody reads before
+                        // anybody writes, and a pass only writes its own range.  118 of the 128 lane slots carry body
+                        // outputs; slots 118..123 (lanes 22..27 of the last pass) take the two strips, three lanes each,
+                        // and store their results themselves -- one code path, different base pointers (like k_fir_tma).
+                        // At the end of a TF a fifth pass turns strip A into "samples 2004..2047 ++ zeros": the symbol's
+                        // own last 44 outputs, whose window runs into zeros (FIRFilter.cpp:186-191).
 #pragma unroll 1
-                        for (int pass = 0; pass < 4; pass++) {
-                            const int k0 = 17 * (32 * pass + lane);
+                        for (int pass = ghost ? 3 : 0; pass < (tf_end ? 5 : 4); pass++) {
+                            const bool extra = pass == 4;
+                            if (extra) {
+                                __syncwarp();
+                                for (int i = lane; i < 44; i += 32) strip[44 + i] = make_float2(0.f, 0.f);
+                                __syncwarp();
+                            }
+                            const int slot = 32 * (extra ? 3 : pass) + lane;
+                            const int sl = slot - 118;                  // >= 0: a strip lane
+                            const int which = sl / 3, k0 = sl >= 0 ? 17 * (sl - 3 * which) : 17 * slot;
+                            const bool on = sl < 0 ? (!ghost && !extra)
+                                                   : extra ? which == 0 : which == 0 ? !ghost : which == 1 ? have_carry : false;
                             float2 acc[17];
 #pragma unroll
                             for (int m = 0; m < 17; m++) acc[m] = make_float2(0.f, 0.f);
-                            const bool on = k0 + 16 < 2004;
                             if (on) {
-                                const float2 *x = xb + k0;
+                                const float2 *x = (sl < 0 ? xb : strip + 88 * which) + k0;
 #pragma unroll
                                 for (int i = 0; i < 17 + 45 - 1; i++) {
                                     const float2 v = x[i];
@@ -408,36 +456,33 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                             }
                             __syncwarp();
                             if (on) {
+                                float2 *dst;
+                                int lim;
+                                if (sl < 0) { dst = xb + k0; lim = 2004 - k0; }
+                                else {
+                                    lim = 44 - k0;
+                                    if (extra) dst = outp + pos + pre + 2004 + k0;                          // end of the TF
+                                    else if (which == 0) dst = outp + pos + (pre - 44) + k0;                // prefix/body seam
+                                    else if (s == 1) dst = outp + out_base + (p.null_size - 44) + k0;      // end of the null symbol
+                                    else dst = outp + (pos - p.sym_size) + pre + 2004 + k0;                 // the previous symbol's tail
+                                }
 #pragma unroll
-                                for (int m = 0; m < 17; m++) xb[k0 + m] = acc[m];
+                                for (int m = 0; m < 17; m++)
+                                    if (m < lim) dst[m] = acc[m];
                             }
                         }
-                        {
-                            // the two 44-output seams: 3 outputs per lane
-                            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
-                            const float2 *x = xb + 3 * lane;
-#pragma unroll
-                            for (int i = 0; i < 47; i++) {
-                                const float2 v = x[i + 1900 - 3 * 16];
-                                if (i < 45) a0 = __ffma2_rn(v, pw.taps[i], a0);
-                                if (i >= 1 && i < 46) a1 = __ffma2_rn(v, pw.taps[i - 1], a1);
-                                if (i >= 2) a2 = __ffma2_rn(v, pw.taps[i - 2], a2);
-                            }
-                            __syncwarp();
-                            sm.code[warp][0] = 0;
-                            float2 *sb = reinterpret_cast<float2 *>(sm.code[warp]);
-                            sb[3 * lane] = a0; sb[3 * lane + 1] = a1; sb[3 * lane + 2] = a2;
-                        }
+                        carry0 = nc0; carry1 = nc1;
+                        have_carry = s != L;
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lane == 0 && !ghost) {
                         if (FUSE) {
+                            // body outputs 0..2003, and the prefix: its outputs 0..459 ARE the body outputs 1544..2003
+                            // (same operands in the same order)
                             float2 *gout = reinterpret_cast<float2 *>(p.out) + pos;
                             sw_bulk_store(gout + pre, xb, 2004 * (int)sizeof(float2));
-                            sw_bulk_store(gout + 44, xb + 1544, 460 * (int)sizeof(float2));
-                            sw_bulk_store(gout, reinterpret_cast<float2 *>(sm.code[warp]), 44 * (int)sizeof(float2));
-                            sw_bulk_store(gout + pre + 2004, reinterpret_cast<float2 *>(sm.code[warp]) + 44, 44 * (int)sizeof(float2));
+                            sw_bulk_store(gout, xb + 1544, (pre - 44) * (int)sizeof(float2));
                         }
                         else if (pw.compact) {
                             float2 *gout = reinterpret_cast<float2 *>(p.out) + ((size_t)tf * L + (s - 1)) * N;

@@ -107,6 +107,36 @@ def test_fir_symbol_kernel(dm, rng, kw):
         assert np.array_equal(a.process(bits[i]).view(np.uint8), ya[i].view(np.uint8)), i
 
 
+@pytest.mark.parametrize("n_tf,kw", [(1, {}), (3, {}), (7, dict(gain_mode="max")), (40, {}), (64, dict(output_rate=8192000)),
+                                     (3, dict(tii=(3, 20)))])
+def test_fir_fused_into_the_symbol_kernel(dm, rng, n_tf, kw):
+    """`fir_kernel` = 3: the 45-tap FIR runs inside k_symbols_w on the staged symbol (symbols_warp.cuh, FUSE); the tail
+    of a symbol is finished one iteration later from carried samples, a warp whose range ends inside a TF assembles
+    one symbol more.  Same operands in the same order as k_fir: the same BITS, whatever the batch size (few TFs: most
+    warps idle or with one symbol; many: ranges that end anywhere in a TF)."""
+    bits = bits_for(rng, 1, n_tf)
+    taps = oracle.fir_default_taps()
+    ref = dm.Modulator(mode=1, fir_taps=taps, max_batch=n_tf, **kw)
+    ref.set_param("fir_kernel", 0)
+    want = ref.process_batch(bits)
+    f = dm.Modulator(mode=1, fir_taps=taps, max_batch=n_tf, **kw)
+    f.set_param("fir_kernel", 3)
+    f.set_param("profile", 1)
+    got = f.process_batch(bits)
+    names = [k for k, _ in f.kernel_times()]
+    if "tii" in kw:
+        assert "k_symbols_w_fir" not in names          # TII frames: the null symbol is not zero, the two-kernel path runs
+    else:
+        assert "k_symbols_w_fir" in names and not any(k.startswith("k_fir") for k in names)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    # a second call on the same handle, and frame by frame
+    assert np.array_equal(f.process_batch(bits).view(np.uint8), want.view(np.uint8)) or "output_rate" in kw or "tii" in kw
+    if "output_rate" not in kw and "tii" not in kw and n_tf <= 7:
+        f.reset()
+        for i in range(n_tf):
+            assert np.array_equal(f.process(bits[i]).view(np.uint8), want[i].view(np.uint8)), i
+
+
 @pytest.mark.parametrize("ntaps", [1, 2, 16, 17, 33, 64, 97, 128])
 def test_fir_tap_counts(dm, rng, ntaps):
     bits = bits_for(rng, 2, 1)
