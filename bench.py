@@ -943,6 +943,25 @@ def gpu_arm(args):
     mod.set_param("profile", 0)
     kavg = {k: float(np.mean(v)) for k, v in ktimes.items()}
 
+    # ---- the same step as two kernels (fir_kernel = 2: k_symbols_w in its compact layout + k_fir_tma), for comparison:
+    #      the fused kernel (fir_kernel = 3, the default) does not write and re-read the 1.245 MB/TF intermediate ----
+    two_kernel = None
+    if rank == 0:
+        try:
+            mod.set_param("fir_kernel", 2)
+            mod.set_param("profile", 1)
+            kt2 = {}
+            for i in range(reps + 2):
+                step_device(i)
+                torch.cuda.synchronize()
+                if i >= 2:
+                    for name, t in mod.kernel_times():
+                        kt2.setdefault(name, []).append(t)
+            two_kernel = {k: float(np.mean(v)) for k, v in kt2.items()}
+        finally:
+            mod.set_param("profile", 0)
+            mod.set_param("fir_kernel", 3)
+
     # ---- end to end through the host-buffer C ABI: `e2e` ----
     for _ in range(max(1, min(args.warmup, 3))):
         step_e2e()
@@ -990,6 +1009,7 @@ def gpu_arm(args):
 
     peak, peak_src = measured_peaks()
     bytes_per_launch = {"k_symbols": SYM_BYTES_PER_TF * n_tf, "k_symbols_w": SYM_BYTES_PER_TF * n_tf,
+                        "k_symbols_w_fir": SYM_BYTES_PER_TF * n_tf,      # bits in, filtered I/Q out: nothing in between
                         "k_fir": FIR_BYTES_PER_TF * n_tf, "k_fir_sym": FIR_SYM_BYTES_PER_TF * n_tf,
                         "k_fir_tma": FIR_SYM_BYTES_PER_TF * n_tf}
     if "k_fir_sym" in kavg or "k_fir_tma" in kavg:
@@ -1004,8 +1024,29 @@ def gpu_arm(args):
         "all_kernels": {k: {"ms": kavg[k], "GB/s": bytes_per_launch[k] / (kavg[k] * 1e-3) / 1e9,
                             "frac": bytes_per_launch[k] / (kavg[k] * 1e-3) / 1e9 / peak} for k in kavg},
     }
+    if dom == "k_symbols_w_fir":
+        # The fused kernel is bound by the FP32 pipe, not by HBM: per TF 35.4 MFLOP of FIR + 8.6 MFLOP of IFFT +
+        # 0.95 MFLOP of gain statistics against 1.6 MB of compulsory traffic = 28 flop/B, the ridge of
+        # this GPU being 72 TFLOP/s / 6.55 TB/s = 11 flop/B.  Both roofs are reported; `frac` above is the HBM one.
+        flops = (35.4e6 + 8.6e6 + 0.95e6) * n_tf
+        tf = flops / (kavg[dom] * 1e-3) / 1e12
+        roofline["fp32"] = {"achieved": tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP32_PEAK_TFLOPS,
+                            "peak_source": "measured FFMA rate, profiles/r01_ubench_fp32_pipes.txt",
+                            "algorithmic_flops_per_launch": flops}
+        roofline["binding_roof"] = "fp32"
+    if two_kernel:
+        b2 = {"k_symbols_w": (TF_IN_BYTES + COMPACT_SAMPLES * 8) * n_tf, "k_fir_tma": FIR_SYM_BYTES_PER_TF * n_tf,
+              "k_fir_sym": FIR_SYM_BYTES_PER_TF * n_tf}
+        roofline["two_kernel_step"] = {
+            "how": "the same step with fir_kernel = 2 (symbol kernel -> compact intermediate in HBM -> k_fir_tma)",
+            "ms": sum(two_kernel.values()),
+            "kernels": {k: {"ms": v, "GB/s": b2.get(k, 0) / (v * 1e-3) / 1e9, "frac": b2.get(k, 0) / (v * 1e-3) / 1e9 / peak}
+                        for k, v in two_kernel.items()},
+            "bytes_moved_per_step": sum(b2.get(k, 0) for k in two_kernel),
+        }
     if not args.no_extras:
-        roofline["traffic"], roofline["traffic_source"] = measure_traffic(dom)
+        # ("k_symbols_w_fir" is the timing label of the FUSE instance of the function k_symbols_w)
+        roofline["traffic"], roofline["traffic_source"] = measure_traffic("k_symbols_w" if dom == "k_symbols_w_fir" else dom)
     if roofline["traffic"] is None:
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):

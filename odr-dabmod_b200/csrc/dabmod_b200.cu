@@ -200,7 +200,8 @@ struct dabmod_b200 {
     DevBuf<float> d_twiddle_w;     // second-pass table of k_symbols_w (TM I only)
     bool use_warp_kernel = true;   // "sym_kernel" knob: 0 = always the CTA-per-symbol-group kernel
     bool use_fir_sym = true;       // "fir_kernel" knob: 0 = always the sample-stream FIR kernel
-    int fir_kernel = 2;            //   1 = k_fir_sym, 2 = k_fir_tma where it applies (complexf output)
+    int fir_kernel = 3;            //   1 = k_fir_sym, 2 = k_fir_tma where it applies (complexf output),
+                                   //   3 = inside the symbol kernel where that applies (k_symbols_w FUSE), else like 2
     int n_twiddle = 0;
     DevBuf<uint16_t> d_tii_bin;
     DevBuf<float> d_tii_val;
