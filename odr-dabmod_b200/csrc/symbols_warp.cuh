@@ -27,10 +27,20 @@ namespace dabmod {
 
 constexpr int SW_WARPS = 12;                // warps (= symbols in flight) per CTA
 constexpr int SW_THREADS = SW_WARPS * 32;
-#ifndef SW_GROUPS_N
-#define SW_GROUPS_N 2
+// Grouping of the twelve warps (see the kernel): -1 = three groups ACROSS the sub-partitions (every sub-partition hosts
+// one warp of each group), 1 = all warps in step, 2 / 4 = groups on DISJOINT sub-partitions.
+#ifndef SW_GROUPS_PLAIN
+#define SW_GROUPS_PLAIN (-1)
 #endif
-constexpr int SW_GROUPS = SW_GROUPS_N;      // 1: all warps in step; 2 / 4: groups of warps on the same sub-partitions, staggered
+#ifndef SW_GROUPS_FUSE
+#define SW_GROUPS_FUSE 2
+#endif
+__device__ __forceinline__ constexpr int sw_n_groups(int mode) { return mode < 0 ? 3 : mode; }
+// a warp's scheduler (SM sub-partition) is warp % 4
+__device__ __forceinline__ int sw_group_of(int warp, int mode)
+{
+    return mode < 0 ? (warp >> 2) : mode == 4 ? (warp & 3) : mode == 2 ? ((warp >> 1) & 1) : 0;
+}
 constexpr int SW_XPAD = 65;                 // lane stride (complex) of the exchange buffer
 constexpr int SW_N = 2048, SW_K = 1536;
 constexpr int SW_CPL = SW_K / 32;           // 48 source carriers per lane
@@ -160,19 +170,24 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
 
     float2 *xb = sm.x[warp];
     uint8_t *code = sm.code[warp];
-    // The warps walk through their symbols in step (one named barrier per symbol): the loop
-    // body is ~50 KB of straight-line code, far beyond the instruction cache, and warps at
-    // different places in it would each stream it separately (measured: 1.03 ms free-running,
-    // 0.62 ms in step).  SW_GROUPS == 2 splits them into two groups half a symbol apart so
-    // that one group's store/scatter latency overlaps the other's butterflies; the second
-    // instruction stream costs more than the overlap gains (0.65 ms) -- when the groups are warps 0-5 and 6-11, which
-    // puts both streams on every sub-partition.  With the groups on DISJOINT sub-partitions (a warp's scheduler is
-    // warp % 4: group = bit 1 of the warp index) each sub-partition's instruction cache follows one stream and the
-    // overlap pays: 0.461 -> 0.430 ms per 1024 TFs (four groups, one per sub-partition: 0.440 ms).
+    // The loop body is ~50 KB of straight-line code, far beyond the 32 KB instruction cache: warps at different
+    // places in it each stream it from L2 (measured: 1.03 ms free-running, 0.62 ms with all twelve in step on one named
+    // barrier per symbol).  In step, however, everybody scatters and exchanges at the same time (LSU busy, FP32 idle)
+    // and then everybody runs butterflies.  Groups of warps that are in step among themselves and apart from each other
+    // overlap the phases at the price of one instruction stream per group; WHERE the groups sit matters (a warp's
+    // scheduler is warp % 4), measured per 1024 TFs, compact layout:
+    //   one group                                                       0.461 ms
+    //   two groups, warps 0-5 / 6-11 (both streams on every sub-partition, round 2 first attempt)  slower than one
+    //   two groups on disjoint sub-partitions (bit 1 of the warp index)  0.430 ms
+    //   four groups, one per sub-partition                              0.440 ms
+    //   three groups ACROSS the sub-partitions (warp / 4: every sub-partition hosts one warp of each group, so its
+    //   warps are in three different phases)                             0.397 ms   <- plain kernel
+    // With the FIR inside (FUSE) the order is reversed -- 0.953 ms across, 0.923 ms disjoint: the filter phase
+    // saturates the FP32 pipe of the sub-partitions it runs on whatever the others do.
+    constexpr int GMODE = FUSE ? SW_GROUPS_FUSE : SW_GROUPS_PLAIN;
+    constexpr int SW_GROUPS = sw_n_groups(GMODE);
     constexpr int GRP_THREADS = SW_THREADS / SW_GROUPS;
-    // a warp's scheduler (SM sub-partition) is warp % 4: a group keeps to its own sub-partitions, so that each
-    // sub-partition's instruction cache follows ONE instruction stream
-    const int grp = SW_GROUPS == 4 ? (warp & 3) : SW_GROUPS == 2 ? ((warp >> 1) & 1) : 0;
+    const int grp = sw_group_of(warp, GMODE);
     bool first_iter = true;
 
     // Work split: the batch is one sequence of n_tf * L transformed symbols (symbol s = 1..L of
@@ -233,10 +248,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     {
         for (int it = 0; it < per_warp + (FUSE ? 1 : 0); it++) {
             sw_bar_sync(1 + grp, GRP_THREADS);
-#ifndef SW_STAGGER_NS
-#define SW_STAGGER_NS (2500u * 4u / SW_GROUPS)
-#endif
-            if (SW_GROUPS > 1 && first_iter && grp > 0) __nanosleep(SW_STAGGER_NS * grp);   // start the groups apart
+            if (SW_GROUPS > 1 && first_iter && grp > 0) __nanosleep((FUSE ? 10000u : 18000u) / SW_GROUPS * grp);   // start the groups apart
             const long long g = g0 + it;
             const bool ghost = FUSE && need_ghost && g == g1;
             const bool fft_symbol = g < g1 || ghost;

@@ -169,10 +169,14 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_wg(const __grid_const
     }
 
     // in step within a group of warps that share their sub-partitions, the groups apart (see k_symbols_w)
-    const int grp = SW_GROUPS == 4 ? (warp & 3) : SW_GROUPS == 2 ? ((warp >> 1) & 1) : 0;
+#ifndef SWG_GROUPS
+#define SWG_GROUPS (-1)
+#endif
+    constexpr int SW_GROUPS = sw_n_groups(SWG_GROUPS);
+    const int grp = sw_group_of(warp, SWG_GROUPS);
     for (int it = 0; it < per_warp; it++) {
         sw_bar_sync(1 + grp, SW_THREADS / SW_GROUPS);        // the warps walk through the loop body in step (instruction cache)
-        if (SW_GROUPS > 1 && it == 0 && grp > 0) __nanosleep(2500u * 4u / SW_GROUPS * grp);
+        if (SW_GROUPS > 1 && it == 0 && grp > 0) __nanosleep(18000u / SW_GROUPS * grp);
         const long long g = g0 + it;
         const bool live_group = g < g1;
         const int tf = live_group ? (int)(g / NG) : 0;

@@ -1,9 +1,7 @@
 #!/bin/bash
-# Experiment: k_symbols_w[_fir] with its warps in 1 / 2 / 4 staggered groups aligned to the SM sub-partitions,
-# and different staggers.  Builds the variants HERE (no GPU needed): bash tools/sw_groups_exp.sh build
-# Times them on the GPU box:                                        bash tools/sw_groups_exp.sh run
+# Experiment: grouping of k_symbols_w's warps.  build here, run on the GPU box.
 cd "$(dirname "$0")/.."
-VARIANTS="g4:-DSW_GROUPS_N=4 g2s2:-DSW_GROUPS_N=2,-DSW_STAGGER_NS=2500u g2s10:-DSW_GROUPS_N=2,-DSW_STAGGER_NS=10000u g4s5:-DSW_GROUPS_N=4,-DSW_STAGGER_NS=5000u"
+VARIANTS="a3:-DSW_GROUPS_N=3,-DSW_GROUPS_ACROSS,-DSW_STAGGER_NS=6000u a2:-DSW_GROUPS_N=2,-DSW_GROUPS_ACROSS,-DSW_STAGGER_NS=9000u"
 if [ "$1" = "build" ]; then
   mkdir -p odr-dabmod_b200/exp
   for v in $VARIANTS; do
