@@ -1,6 +1,7 @@
 // k_symbols_wg: the warp-per-symbol structure of k_symbols_w (symbols_warp.cuh) for TM IV (N = 1024) and TM II
 // (N = 512) as "64 / R1 symbols per warp", R1 = N / 32.  (TM III, N = 256, 8 symbols per warp with an odd sample
-// count per symbol, was built and measured at 0.66 ms per 4096 TFs -- no faster than k_symbols, which it keeps.)
+// count per symbol -- so plain stores instead of bulk copies -- was built and measured twice: 0.66 ms per 4096 TFs with
+// the warps in step, 0.70 ms with them in three groups; k_symbols runs it in 0.65 ms and keeps it.)
 //
 // Same chain and the same reference lines as k_symbols_w (QpskSymbolMapper.cpp:105-156,
 // FrequencyInterleaver.cpp:103-126, DifferentialModulator.cpp:45-76, SignalMultiplexer.cpp:45-71,
