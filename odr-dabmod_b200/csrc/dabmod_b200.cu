@@ -201,7 +201,8 @@ struct dabmod_b200 {
     bool use_warp_kernel = true;   // "sym_kernel" knob: 0 = always the CTA-per-symbol-group kernel
     bool use_fir_sym = true;       // "fir_kernel" knob: 0 = always the sample-stream FIR kernel
     int fir_kernel = 3;            //   1 = k_fir_sym, 2 = k_fir_tma where it applies (complexf output),
-                                   //   3 = inside the symbol kernel where that applies (k_symbols_w FUSE), else like 2
+                                   //   3 = inside the symbol kernel where that applies (k_symbols_w FUSE) and pays
+                                   //   (batch size), else like 2; 4 = 3 at any batch size
     int n_twiddle = 0;
     DevBuf<uint16_t> d_tii_bin;
     DevBuf<float> d_tii_val;
@@ -594,7 +595,11 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         const long long n_sym = (long long)n_tf * m.L;
         const int wgrid = (int)std::min<long long>((n_sym + SW_WARPS - 1) / SW_WARPS, h->sm_count);
         // "fir_kernel" = 3: the 45-tap FIR inside the symbol kernel (complexf out of the FIR stage; symbols_warp.cuh FUSE)
-        const bool fused = compact && !post && h->fir_kernel >= 3;
+        // (from eight symbols per warp on: below that the one symbol more that a warp assembles to finish its range
+        // -- see the kernel -- outweighs the saved intermediate; measured 64 / 128 TFs: two kernels 2-4 % faster)
+        // ("fir_kernel" = 4: at any batch size -- the tests walk the kernel's edge cases with few frames)
+        const bool fused = compact && !post &&
+                           (h->fir_kernel >= 4 || (h->fir_kernel == 3 && (long long)n_tf * m.L >= 8LL * h->sm_count * SW_WARPS));
         ProfScope prof_w(h, fused ? "k_symbols_w_fir" : "k_symbols_w", s);
         if (fused) {
             for (size_t j = 0; j < 45 && j < h->fir_taps.size(); j++) wp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);

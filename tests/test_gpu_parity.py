@@ -65,8 +65,7 @@ def test_fir_default_taps(dm, rng, mode):
     out = mod.process_batch(bits)
     for i in range(2):
         assert rel_rms(out[i], ora[i]) < TOL
-    # TM I: the filter runs inside the symbol kernel (one launch); the other modes: symbol kernel + k_fir
-    assert mod.last_launch_count == (1 if mode == 1 else 2)
+    assert mod.last_launch_count == 2      # symbol kernel + FIR kernel (two frames: too few for the fused TM I kernel)
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(fmt="s16", digital_gain=0.7), dict(gain_mode="max"),
@@ -110,7 +109,8 @@ def test_fir_symbol_kernel(dm, rng, kw):
 
 
 @pytest.mark.parametrize("n_tf,kw", [(1, {}), (3, {}), (7, dict(gain_mode="max")), (40, {}), (64, dict(output_rate=8192000)),
-                                     (3, dict(tii=(3, 20)))])
+                                     (3, dict(tii=(3, 20))), (200, {}), (333, dict(gain_mode="fix")),
+                                     (256, dict(output_rate=8192000))])
 def test_fir_fused_into_the_symbol_kernel(dm, rng, n_tf, kw):
     """`fir_kernel` = 3: the 45-tap FIR runs inside k_symbols_w on the staged symbol (symbols_warp.cuh, FUSE); the tail
     of a symbol is finished one iteration later from carried samples, a warp whose range ends inside a TF assembles
@@ -122,7 +122,7 @@ def test_fir_fused_into_the_symbol_kernel(dm, rng, n_tf, kw):
     ref.set_param("fir_kernel", 0)
     want = ref.process_batch(bits)
     f = dm.Modulator(mode=1, fir_taps=taps, max_batch=n_tf, **kw)
-    f.set_param("fir_kernel", 3)
+    f.set_param("fir_kernel", 4)                     # (3, the default, only fuses from 8 symbols per warp on)
     f.set_param("profile", 1)
     got = f.process_batch(bits)
     names = [k for k, _ in f.kernel_times()]
@@ -130,6 +130,9 @@ def test_fir_fused_into_the_symbol_kernel(dm, rng, n_tf, kw):
         assert "k_symbols_w_fir" not in names          # TII frames: the null symbol is not zero, the two-kernel path runs
     else:
         assert "k_symbols_w_fir" in names and not any(k.startswith("k_fir") for k in names)
+        # the default (3) decides per launch -- the host entry point works in slices of ~30 TFs -- and gives the same bits
+        d = dm.Modulator(mode=1, fir_taps=taps, max_batch=n_tf, **kw)
+        assert np.array_equal(d.process_batch(bits).view(np.uint8), want.view(np.uint8))
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
     # a second call on the same handle, and frame by frame
     assert np.array_equal(f.process_batch(bits).view(np.uint8), want.view(np.uint8)) or "output_rate" in kw or "tii" in kw
