@@ -17,6 +17,7 @@ OUT = os.path.join(ROOT, "profiles", "sass")
 # (file stem, mangled-name regex, keep the full listing?)
 KERNELS = [
     ("k_symbols_w", r"k_symbols_wILb0ELb0E", False),
+    ("k_symbols_w_fir", r"k_symbols_wILb0ELb1E", True),      # the headline kernel: symbol kernel with the FIR inside
     ("k_symbols_wg_tm4", r"k_symbols_wgILi32ELb0E", False),
     ("k_fir_tma", r"k_fir_tmaILi45E", True),
     ("k_resample_up3_L4", r"k_resample_up3ILb0ELi4E", True),
