@@ -248,7 +248,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     {
         for (int it = 0; it < per_warp + (FUSE ? 1 : 0); it++) {
             sw_bar_sync(1 + grp, GRP_THREADS);
-            if (SW_GROUPS > 1 && first_iter && grp > 0) __nanosleep((FUSE ? 10000u : 18000u) / SW_GROUPS * grp);   // start the groups apart
+#ifndef SW_STAGGER_PLAIN_NS
+#define SW_STAGGER_PLAIN_NS 6000u
+#endif
+            if (SW_GROUPS > 1 && first_iter && grp > 0) __nanosleep((FUSE ? 5000u : SW_STAGGER_PLAIN_NS) * grp);   // start the groups apart
             const long long g = g0 + it;
             const bool ghost = FUSE && need_ghost && g == g1;
             const bool fft_symbol = g < g1 || ghost;
