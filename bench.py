@@ -1098,8 +1098,8 @@ def gpu_arm(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "mode": MODE, "tfs_per_step_per_gpu": n_tf,
                    "eti_frames_per_step": eti_per_step, "output": "complexf", "gain": "var",
-                   "l2": "per-step working set 2.9 GB (1.3 GB symbol-stage, compact layout + 1.6 GB output) >> 126 MB L2; "
-                         "input bits rotate over 4 buffers",
+                   "l2": "inputs larger than L2: per step 1.6 GB of output written and 29 MB of input read (one fused kernel, "
+                         "no intermediate) >> 126 MB L2; input bits rotate over 4 buffers",
                    "parallelism": "frame-sharded x%d, no collective" % world},
         "e2e": {"value": e2e_value, "unit": "ETI frames/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "checksum": checksum,
