@@ -13,7 +13,31 @@ from conftest import rel_rms, write_poly_file
 from oracle import refwrap
 
 have = refwrap.available() and refwrap.available("b1")
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have, reason="oracle/_ref libraries not built (make -C oracle ref b1)")]
+needs_libs = pytest.mark.skipif(not have, reason="oracle/_ref libraries not built (make -C oracle ref b1)")
+pytestmark = [needs_libs]
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="needs a host without a GPU")
+def test_substituted_blocks_have_no_cpu_fallback(rng):
+    """CPU: the library links (every reference symbol the harness needs is defined by B200Blocks.cpp), the graph
+    builds, the tokens pass the pipelined blocks (empty calls while they prime) -- and the first frame that reaches
+    OutputMemory fails with the C ABI's error instead of being computed on the host."""
+    b1 = refwrap.RefChain(variant="b1", mode=2, fir_taps_file="default")
+    assert b1.latency == 2                                     # GainControl + FIRFilter, like the reference graph
+    bits = rng.integers(0, 256, refwrap.TF_BYTES[2], dtype=np.uint8)
+    for _ in range(b1.latency):
+        assert b1.feed(bits).size == 0
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        b1.feed(bits)
+    b1.close()
 
 CASES = {
     "tm1_var": dict(mode=1),
@@ -37,6 +61,7 @@ CASES = {
 }
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_substituted_blocks_against_the_reference_blocks(rng, tmp_path, case):
     kw = dict(CASES[case])
@@ -86,6 +111,7 @@ def test_substituted_blocks_against_the_reference_blocks(rng, tmp_path, case):
     b1.close()
 
 
+@pytest.mark.gpu
 def test_two_graphs_side_by_side(rng):
     """Two graphs built before either runs (different modes), frames interleaved: the token keeps them apart."""
     a = refwrap.RefChain(variant="b1", mode=1, fir_taps_file="default")
