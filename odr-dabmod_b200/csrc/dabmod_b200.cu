@@ -210,6 +210,7 @@ struct dabmod_b200 {
     DevBuf<float> d_lut;
     DevBuf<float> d_fir_taps;      // taps of a filter longer than MAX_FIR_TAPS (k_fir_long), zero padded
     DevBuf<float2> d_tii_frame;    // one frame through k_symbols: its null symbol is the stream's TII symbol (k_tii_fill)
+    DevBuf<float2> d_tii_fir;      // ... and the same through the FIR: the filtered null symbol of a TII frame (fused kernel)
     DevBuf<uint8_t> d_tii_bits;    // that frame's (all-zero) input block
     DevBuf<unsigned long long> d_clipped;
     int tii_count = 0;
@@ -584,6 +585,30 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
     // ... followed by the default-length FIR: the symbol kernel leaves out null symbol and cyclic prefix,
     // k_fir_sym works symbol by symbol on that compact layout (kernels.cuh); not with TII (the null symbol is not zero)
     const bool compact = warp_kernel && fir && h->fir_taps.size() == 45 && h->use_fir_sym && h->tii_count == 0;
+    // one frame through the general kernel: its null symbol is the stream's TII symbol (see k_tii_fill)
+    auto make_tii_frame = [&]() {
+        if (!h->d_tii_frame.p) {
+            h->d_tii_frame.alloc((size_t)m.tf_samples);
+            h->d_tii_bits.alloc((size_t)m.tf_in_bytes);
+            CUDA_CHECK(cudaMemsetAsync(h->d_tii_bits.p, 0, (size_t)m.tf_in_bytes, s));
+        }
+        SymParams tp = sp;
+        tp.bits = h->d_tii_bits.p;
+        tp.out = h->d_tii_frame.p;
+        tp.tf_offset = 0;                               // frame 0 of a stream carries the TII symbol
+        tp.post = PostParams{};
+        tp.groups_per_chunk = 2;                        // the null symbol and symbol 1 are all that is needed
+        tp.n_chunks = 1;
+        ProfScope prof_t(h, "k_symbols", s);
+        switch (m.N) {
+            case 2048: launch_symbols_n<2048>(tp, false, false, 1, s); break;
+            case 1024: launch_symbols_n<1024>(tp, false, false, 1, s); break;
+            default: launch_symbols_n<512>(tp, false, false, 1, s); break;
+        }
+        CUDA_CHECK(cudaGetLastError());
+        prof_t.end();
+        launches++;
+    };
     // TM I without the optional per-carrier features: one warp per symbol (symbols_warp.cuh)
     if (warp_kernel) {
         SymWParams wp{};
@@ -598,8 +623,32 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
         // (from eight symbols per warp on: below that the one symbol more that a warp assembles to finish its range
         // -- see the kernel -- outweighs the saved intermediate; measured 64 / 128 TFs: two kernels 2-4 % faster)
         // ("fir_kernel" = 4: at any batch size -- the tests walk the kernel's edge cases with few frames)
-        const bool fused = compact && !post &&
+        // With TII the null symbol of every second frame is one constant vector per stream: its filtered samples
+        // (all but the last 44, which see symbol 1) are computed once per call -- one frame through k_symbols and
+        // k_fir -- and copied into the TII frames; the fused kernel takes the symbol's last 44 samples as the carry
+        // into symbol 1 instead of zeros.
+        const bool fused = warp_kernel && fir && h->fir_taps.size() == 45 && h->use_fir_sym && !post &&
+                           (h->tii_count == 0 || tii_fill) &&
                            (h->fir_kernel >= 4 || (h->fir_kernel == 3 && (long long)n_tf * m.L >= 8LL * h->sm_count * SW_WARPS));
+        if (fused && h->tii_count > 0) {
+            make_tii_frame();
+            if (!h->d_tii_fir.p) h->d_tii_fir.alloc((size_t)m.tf_samples);
+            FirParams fp{};
+            fp.in = h->d_tii_frame.p;
+            fp.out = h->d_tii_fir.p;
+            fp.tf_samples = m.tf_samples;
+            fp.tiles_per_tf = (m.null_size + FIR_TILE - 1) / FIR_TILE;      // the tiles that cover the null symbol
+            fp.ntaps = 45;
+            std::memset(fp.taps, 0, sizeof(fp.taps));
+            for (size_t j = 0; j < 45; j++) fp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
+            fp.post = PostParams{};
+            ProfScope prof_tf(h, "k_fir", s);
+            launch_fir_p<false>(fp, 45, fp.tiles_per_tf, s);
+            CUDA_CHECK(cudaGetLastError());
+            prof_tf.end();
+            launches++;
+            wp.tii_tail = h->d_tii_frame.p + (m.null_size - 44);
+        }
         ProfScope prof_w(h, fused ? "k_symbols_w_fir" : "k_symbols_w", s);
         if (fused) {
             for (size_t j = 0; j < 45 && j < h->fir_taps.size(); j++) wp.taps[j] = make_float2(h->fir_taps[j], h->fir_taps[j]);
@@ -611,6 +660,15 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
             CUDA_CHECK(cudaGetLastError());
             prof_w.end();
             launches++;
+            if (h->tii_count > 0) {
+                const int fsz = m.null_size - 44;
+                const int fgrid = (int)std::min<size_t>(n_tf * (size_t)((fsz + 255) / 256), (size_t)h->sm_count * 8);
+                ProfScope prof_f(h, "k_tii_fill", s);
+                k_tii_fill<false><<<fgrid, 256, 0, s>>>(h->d_tii_fir.p, dst, fsz, m.tf_samples, (int)n_tf, stream_tf, PostParams{});
+                CUDA_CHECK(cudaGetLastError());
+                prof_f.end();
+                launches++;
+            }
             return;
         }
         if (sym_post) {
@@ -668,27 +726,7 @@ void enqueue_front(dabmod_b200 *h, const uint8_t *d_bits, size_t n_tf, void *dst
 
     if (tii_fill && (warp_kernel || ((m.N == 1024 || m.N == 512) && warp_ok))) {
         // one frame through the general kernel (its null symbol is the TII symbol), then into every TII frame
-        if (!h->d_tii_frame.p) {
-            h->d_tii_frame.alloc((size_t)m.tf_samples);
-            h->d_tii_bits.alloc((size_t)m.tf_in_bytes);
-            CUDA_CHECK(cudaMemsetAsync(h->d_tii_bits.p, 0, (size_t)m.tf_in_bytes, s));
-        }
-        SymParams tp = sp;
-        tp.bits = h->d_tii_bits.p;
-        tp.out = h->d_tii_frame.p;
-        tp.tf_offset = 0;                               // frame 0 of a stream carries the TII symbol
-        tp.post = PostParams{};
-        tp.groups_per_chunk = 2;                        // the null symbol and symbol 1 are all that is needed
-        tp.n_chunks = 1;
-        ProfScope prof_t(h, "k_symbols", s);
-        switch (m.N) {
-            case 2048: launch_symbols_n<2048>(tp, false, false, 1, s); break;
-            case 1024: launch_symbols_n<1024>(tp, false, false, 1, s); break;
-            default: launch_symbols_n<512>(tp, false, false, 1, s); break;
-        }
-        CUDA_CHECK(cudaGetLastError());
-        prof_t.end();
-        launches++;
+        make_tii_frame();
         const int fgrid = (int)std::min<size_t>(n_tf * (size_t)((m.null_size + 255) / 256), (size_t)h->sm_count * 8);
         ProfScope prof_f(h, "k_tii_fill", s);
         if (sym_post) k_tii_fill<true><<<fgrid, 256, 0, s>>>(h->d_tii_frame.p, sp.out, m.null_size, m.tf_samples, (int)n_tf, stream_tf, sp.post);

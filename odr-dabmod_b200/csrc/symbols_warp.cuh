@@ -67,6 +67,7 @@ struct SymWParams {
     const float2 *twiddle_w;                // 31 * 64 entries
     int n_tf;
     float2 taps[45];                        // FUSE: the FIR taps as (tap, tap) pairs
+    const float2 *tii_tail;                 // FUSE with TII: the last 44 samples of the stream's TII null symbol (else nullptr)
     int compact;                            // 1: write only the N samples of every data symbol, back to back
                                             // ([tf][s-1][N], no null symbol, no cyclic prefix): the layout
                                             // k_fir_sym reads (it rebuilds the guard interval itself)
@@ -263,13 +264,20 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
                 // start of a TF.  Null symbol without TII: all-zero carriers -> all-zero samples,
                 // whatever gain it borrows from symbol 1 (GainControl.cpp:139-144).  The
                 // differential chain restarts from the phase reference (DifferentialModulator.cpp:65).
-                if (!pw.compact) {
+                // FUSE with TII: every second frame of the stream (TII.cpp:225-242) starts with the TII symbol, one constant
+                // vector: k_tii_fill writes its filtered samples, and its last 44 samples are what symbol 1's prefix follows
+                const bool tii_frame = FUSE && pw.tii_tail != nullptr && ((p.tf_offset + (unsigned long long)tf) & 1ull) == 0;
+                if (!pw.compact && !tii_frame) {
                     // (FUSE: the last 44 samples of the filtered null symbol see the first prefix, see below)
                     for (int i = lane; i < p.null_size - (FUSE ? 44 : 0); i += 32)
                         store_sample<POST>(p.out, out_base + i, make_float2(0.f, 0.f), p.post, clip);
                 }
                 if (FUSE) {
                     carry0 = carry1 = make_float2(0.f, 0.f);        // the null symbol ends in zeros
+                    if (tii_frame && lane < 22) {
+                        carry0 = __ldg(pw.tii_tail + 2 * lane);
+                        carry1 = __ldg(pw.tii_tail + 2 * lane + 1);
+                    }
                     have_carry = true;
                 }
 #pragma unroll

@@ -109,7 +109,8 @@ def test_fir_symbol_kernel(dm, rng, kw):
 
 
 @pytest.mark.parametrize("n_tf,kw", [(1, {}), (3, {}), (7, dict(gain_mode="max")), (40, {}), (64, dict(output_rate=8192000)),
-                                     (3, dict(tii=(3, 20))), (200, {}), (333, dict(gain_mode="fix")),
+                                     (3, dict(tii=(3, 20))), (40, dict(tii=(3, 20))), (33, dict(tii=(7, 5, 1), gain_mode="max")),
+                                     (200, {}), (333, dict(gain_mode="fix")),
                                      (256, dict(output_rate=8192000))])
 def test_fir_fused_into_the_symbol_kernel(dm, rng, n_tf, kw):
     """`fir_kernel` = 3: the 45-tap FIR runs inside k_symbols_w on the staged symbol (symbols_warp.cuh, FUSE); the tail
@@ -126,8 +127,12 @@ def test_fir_fused_into_the_symbol_kernel(dm, rng, n_tf, kw):
     f.set_param("profile", 1)
     got = f.process_batch(bits)
     names = [k for k, _ in f.kernel_times()]
-    if "tii" in kw:
-        assert "k_symbols_w_fir" not in names          # TII frames: the null symbol is not zero, the two-kernel path runs
+    if "tii" in kw and n_tf < 16:
+        assert "k_symbols_w_fir" not in names          # a few TII frames: the general kernel + k_fir
+    elif "tii" in kw:
+        # (k_symbols + k_fir on ONE frame make the stream's filtered TII symbol; the host entry point works in slices,
+        # a last slice below 16 frames takes the general kernels)
+        assert "k_symbols_w_fir" in names and "k_tii_fill" in names
     else:
         assert "k_symbols_w_fir" in names and not any(k.startswith("k_fir") for k in names)
         # the default (3) decides per launch -- the host entry point works in slices of ~30 TFs -- and gives the same bits
@@ -136,6 +141,16 @@ def test_fir_fused_into_the_symbol_kernel(dm, rng, n_tf, kw):
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
     # a second call on the same handle, and frame by frame
     assert np.array_equal(f.process_batch(bits).view(np.uint8), want.view(np.uint8)) or "output_rate" in kw or "tii" in kw
+    if "tii" in kw and n_tf >= 16:
+        # the TII toggle runs on across calls (TII.cpp:225-242): an odd number of frames flips which frames carry it
+        ref.reset()
+        f.reset()
+        a = np.concatenate([ref.process_batch(bits[:17]), ref.process_batch(bits[17:])])
+        b = np.concatenate([f.process_batch(bits[:17]), f.process_batch(bits[17:])])
+        # (against each other: with TII the symbol kernel itself depends on the number of frames in a launch -- the
+        # warp kernels from 16 frames on -- and the two families agree to 1e-7, not to the bit)
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+        assert rel_rms(b.reshape(-1), want.reshape(-1)) < 1e-6
     if "output_rate" not in kw and "tii" not in kw and n_tf <= 7:
         f.reset()
         for i in range(n_tf):
