@@ -23,9 +23,6 @@ for fk in (2, 3, 2, 3):
         mod.process_batch_device(bits.data_ptr(), n, out.data_ptr(), st.cuda_stream)
         torch.cuda.synchronize()
         ts.append(mod.kernel_times())
-    med = {}
-    for k, _ in ts[0]:
-        med[k] = med.get(k, 0.0) + float(np.median([sum(t for kk, t in tt if kk == k) for tt in ts[3:]])) * 0 + 0
     tot = float(np.median([sum(t for _, t in tt) for tt in ts[3:]]))
     names = [k for k, _ in ts[0]]
     print("fir_kernel=%d" % fk, names, "total %.4f ms" % tot, flush=True)
