@@ -15,42 +15,52 @@
 
 namespace dabmod {
 
-// Packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2): one instruction per complex add,
-// same rounding as two scalar operations.  The butterflies are bound by instruction
-// issue, not by the FP32 pipe, so halving the adds is what counts.  Anything that
-// swaps re and im (multiplication by +-j) stays scalar: a packed operand is an aligned
-// register pair and a swap would cost real moves.
+// Packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2): one instruction per complex add, same rounding as two scalar
+// operations.  The butterflies are bound by instruction issue and instruction supply, not by the FP32 pipe, so the
+// instruction count is what counts -- and the packed instructions take their operands through free modifiers
+// (cuobjdump -sass of the intrinsics below):
+//     R.F32x2.LO_HI      the two halves swapped             FADD2 R8, R2.F32x2.HI_LO, -R4.F32x2.LO_HI.NP
+//     -R....NP           ONE half negated                   = a + j b in one instruction
+//     R.F32 / immediate  one 32-bit value for both halves   FMUL2 R8, R2.F32x2.HI_LO, R4.F32
+// so a multiplication by +-j costs nothing (it folds into the consumer's operand), a +- j b is one FADD2, and a full
+// complex product is FMUL2 + FFMA2: two instructions instead of four, no moves.  (Round 1 kept everything that swaps
+// re and im scalar, on the assumption that a swapped register pair costs real moves.)
 #if defined(__CUDA_ARCH__)
 DABMOD_FN float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 DABMOD_FN float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 DABMOD_FN float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
 DABMOD_FN float2 cfma(float s, float2 a, float2 c) { return __ffma2_rn(make_float2(s, s), a, c); }
+// (a.x b.x - a.y b.y, a.y b.x + a.x b.y) = a * (b.x, b.x) + (-a.y, a.x) * (b.y, b.y)
+DABMOD_FN float2 cmul(float2 a, float2 b)
+{
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
 #else
 DABMOD_FN float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 DABMOD_FN float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 DABMOD_FN float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 DABMOD_FN float2 cfma(float s, float2 a, float2 c) { return make_float2(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y)); }
-#endif
 DABMOD_FN float2 cmul(float2 a, float2 b)
 {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.x, b.y, a.y * b.x));     // the device's rounding
 }
-// multiply by +j (INV) or -j (forward)
+#endif
+// multiply by +j (INV) or -j (forward): free when the consumer is a packed instruction
 template <bool INV>
 DABMOD_FN float2 mul_j(float2 a)
 {
     return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
-// a + (+-j) b and a - (+-j) b, component-wise (no swapped operand is materialised)
+// a + (+-j) b and a - (+-j) b: one packed add each
 template <bool INV>
 DABMOD_FN float2 cadd_j(float2 a, float2 b)
 {
-    return INV ? make_float2(a.x - b.y, a.y + b.x) : make_float2(a.x + b.y, a.y - b.x);
+    return cadd(a, mul_j<INV>(b));
 }
 template <bool INV>
 DABMOD_FN float2 csub_j(float2 a, float2 b)
 {
-    return INV ? make_float2(a.x + b.y, a.y - b.x) : make_float2(a.x - b.y, a.y + b.x);
+    return cadd(a, mul_j<!INV>(b));
 }
 // twiddle table holds e^{+j theta}; the forward transform needs the conjugate
 template <bool INV>
@@ -83,8 +93,8 @@ template <int O, bool INV>
 DABMOD_FN float2 mul_w8(float2 a)
 {
     const float h = 0.70710678118654752440f;
-    // (1 + j) a = (a.x - a.y, a.x + a.y);  (1 - j) a = (a.x + a.y, a.y - a.x)
-    const float2 p = make_float2(a.x - a.y, a.x + a.y), m = make_float2(a.x + a.y, a.y - a.x);
+    // (1 + j) a = (a.x - a.y, a.x + a.y);  (1 - j) a = (a.x + a.y, a.y - a.x): one packed add each
+    const float2 p = cadd(a, make_float2(-a.y, a.x)), m = cadd(a, make_float2(a.y, -a.x));
     if (O == 1) return cscale(INV ? p : m, h);
     if (O == 3) return cscale(INV ? make_float2(-m.x, -m.y) : make_float2(-p.x, -p.y), h);
     if (O == 5) return cscale(INV ? make_float2(-p.x, -p.y) : make_float2(-m.x, -m.y), h);
