@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
                 const float2 a = __ldg(src + 256 * r - hi);        // H_{b-1}[m]
                 const float2 b = __ldg(src + 256 * r);             // H_b[m]
                 const float2 c = __ldg(src + 256 * r - 2 * hi);    // H_{b-2}[m]
-                F[r] = make_float2(fmaf(w0, a.x, w1 * a.x), fmaf(w0, a.y, w1 * a.y));
-                F[r + 8] = make_float2(fmaf(w1, b.x, w0 * c.x), fmaf(w1, b.y, w0 * c.y));
+                F[r] = cfma(w0, a, cscale(a, w1));
+                F[r + 8] = cfma(w1, b, cscale(c, w0));
             }
         }
         else {
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(RQ_THREADS, 1) k_resample_q(const __grid_const
                 const float2 a = res_load(p, base - hi + m);
                 const float2 b = res_load(p, base + m);
                 const float2 c = res_load(p, base - 2 * hi + m);
-                F[r] = make_float2(fmaf(w0, a.x, w1 * a.x), fmaf(w0, a.y, w1 * a.y));
-                F[r + 8] = make_float2(fmaf(w1, b.x, w0 * c.x), fmaf(w1, b.y, w0 * c.y));
+                F[r] = cfma(w0, a, cscale(a, w1));
+                F[r + 8] = cfma(w1, b, cscale(c, w0));
             }
         }
         {

@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
                 const float2 a = __ldg(src + 256 * r - hi);        // H_{b-1}[m]
                 const float2 b = __ldg(src + 256 * r);             // H_b[m]
                 const float2 c = __ldg(src + 256 * r - 2 * hi);    // H_{b-2}[m]
-                v[r] = make_float2(fmaf(w0, a.x, w1 * a.x), fmaf(w0, a.y, w1 * a.y));
-                v[r + 8] = make_float2(fmaf(w1, b.x, w0 * c.x), fmaf(w1, b.y, w0 * c.y));
+                v[r] = cfma(w0, a, cscale(a, w1));
+                v[r + 8] = cfma(w1, b, cscale(c, w0));
                 c_lo[r] = v[r];
             }
         }
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
                 const float2 a = res_load(p, base - hi + m);
                 const float2 b = res_load(p, base + m);
                 const float2 c = res_load(p, base - 2 * hi + m);
-                v[r] = make_float2(fmaf(w0, a.x, w1 * a.x), fmaf(w0, a.y, w1 * a.y));
-                v[r + 8] = make_float2(fmaf(w1, b.x, w0 * c.x), fmaf(w1, b.y, w0 * c.y));
+                v[r] = cfma(w0, a, cscale(a, w1));
+                v[r + 8] = cfma(w1, b, cscale(c, w0));
                 c_lo[r] = v[r];
             }
         }
@@ -180,9 +180,8 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
             const float sgn = (t & 1) ? -1.0f : 1.0f;     // (-1)^m, m = t + 256 r has the parity of t
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const float2 y = make_float2(fmaf((float)RU_NI, c_lo[r].x, sgn * ny.x),
-                                             fmaf((float)RU_NI, c_lo[r].y, sgn * ny.y));
-                sm.stage[team][0][t + 256 * r] = make_float2(y.x * p.factor, y.y * p.factor);
+                const float2 y = cfma((float)RU_NI, c_lo[r], cscale(ny, sgn));
+                sm.stage[team][0][t + 256 * r] = cscale(y, p.factor);
             }
         }
         float2 wt = __ldg(p.tw_out + t);      // e^{j 2 pi t rho / No} of the next phase, fetched one phase ahead
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) k_resample_up(const __grid_cons
             ru_fft4096<true>(v, buf, sm.tw2, sm.tw3, t, team);
 #pragma unroll
             for (int r = 0; r < 8; r++)
-                sm.stage[team][rho][t + 256 * r] = make_float2(v[r].x * p.factor, v[r].y * p.factor);
+                sm.stage[team][rho][t + 256 * r] = cscale(v[r], p.factor);
         }
         ru_bar(team);
         // ---- interleave the L phases and store: out[(hop*hi + m) * L + rho] ----
@@ -337,8 +336,8 @@ __global__ void __launch_bounds__(RU3_THREADS, 1) k_resample_up3(const __grid_co
                 const float2 a = __ldg(src + 256 * r - hi);        // H_{b-1}[m]
                 const float2 b = __ldg(src + 256 * r);             // H_b[m]
                 const float2 c = __ldg(src + 256 * r - 2 * hi);    // H_{b-2}[m]
-                v[r] = make_float2(fmaf(w0, a.x, w1 * a.x), fmaf(w0, a.y, w1 * a.y));
-                v[r + 8] = make_float2(fmaf(w1, b.x, w0 * c.x), fmaf(w1, b.y, w0 * c.y));
+                v[r] = cfma(w0, a, cscale(a, w1));
+                v[r + 8] = cfma(w1, b, cscale(c, w0));
                 y0[r] = v[r];
             }
         }
@@ -350,8 +349,8 @@ __global__ void __launch_bounds__(RU3_THREADS, 1) k_resample_up3(const __grid_co
                 const float2 a = res_load(p, base - hi + m);
                 const float2 b = res_load(p, base + m);
                 const float2 c = res_load(p, base - 2 * hi + m);
-                v[r] = make_float2(fmaf(w0, a.x, w1 * a.x), fmaf(w0, a.y, w1 * a.y));
-                v[r + 8] = make_float2(fmaf(w1, b.x, w0 * c.x), fmaf(w1, b.y, w0 * c.y));
+                v[r] = cfma(w0, a, cscale(a, w1));
+                v[r + 8] = cfma(w1, b, cscale(c, w0));
                 y0[r] = v[r];
             }
         }
@@ -376,8 +375,8 @@ __global__ void __launch_bounds__(RU3_THREADS, 1) k_resample_up3(const __grid_co
             const float sgn = (t & 1) ? -1.0f : 1.0f;     // (-1)^m, m = t + 256 r has the parity of t
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const float2 y = make_float2(fmaf((float)RU_NI, y0[r].x, sgn * ny.x), fmaf((float)RU_NI, y0[r].y, sgn * ny.y));
-                y0[r] = make_float2(y.x * p.factor, y.y * p.factor);
+                const float2 y = cfma((float)RU_NI, y0[r], cscale(ny, sgn));
+                y0[r] = cscale(y, p.factor);
             }
         }
         const size_t obase = (size_t)hop * hi * L + (size_t)t * L;     // sample L m of m = t: + 256 r L per r
@@ -408,7 +407,7 @@ __global__ void __launch_bounds__(RU3_THREADS, 1) k_resample_up3(const __grid_co
             wt = __ldg(p.tw_out + t * (rho + 1));
             ru3_fft4096<true>(v, buf, sm.tw2, sm.tw3, t, team);
 #pragma unroll
-            for (int r = 0; r < 8; r++) v[r] = make_float2(v[r].x * p.factor, v[r].y * p.factor);
+            for (int r = 0; r < 8; r++) v[r] = cscale(v[r], p.factor);
             if (pairs) {
                 if (rho & 1) {
                     // y0 holds phase rho - 1: two consecutive output samples per m
