@@ -286,3 +286,26 @@ def test_eti_engine_survives_a_multiplex_reconfiguration(tmp_path):
     for i in range((n2 - 8) // 4 - 1):
         a = out["both"][out["p1"].size + i * per_tf:out["p1"].size + (i + 1) * per_tf]
         assert rel_rms(a, ref[(r1 + i) * per_tf:(r1 + i + 1) * per_tf]) < 2e-6, i
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="the reference tree is only present in the build container")
+def test_patch_engine_anchors_still_match(tmp_path):
+    """CPU (build container): oracle/patch_engine.py finds every anchor in the reference sources exactly once and
+    writes the three patched copies with both engine families in them."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "patch_engine.py"), "/root/reference", str(tmp_path)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    cfg = open(tmp_path / "ConfigParser.cpp").read()
+    mod = open(tmp_path / "DabModulator.cpp").read()
+    main = open(tmp_path / "DabMod.cpp").read()
+    for name in ("b200", "b200_fixed", "b200_eti", "b200_eti_fixed"):
+        assert '"%s"' % name in cfg
+    assert "B200OfdmChain" in mod and "B200EtiChain" in mod and "B200SwapOutput" in mod
+    assert "B200EtiChain::flush_active()" in main
+    # nothing but the anchored edits: the copies differ from the reference in a handful of lines
+    import difflib
+    for name, text in (("ConfigParser.cpp", cfg), ("DabModulator.cpp", mod), ("DabMod.cpp", main)):
+        ref = open(os.path.join("/root/reference/src", name)).read()
+        changed = [l for l in difflib.unified_diff(ref.splitlines(), text.splitlines(), lineterm="", n=0)
+                   if l[:1] in "+-" and l[:3] not in ("+++", "---")]
+        assert 0 < len(changed) < 80, (name, len(changed))
