@@ -33,7 +33,7 @@ constexpr int SW_THREADS = SW_WARPS * 32;
 #define SW_GROUPS_PLAIN (-1)
 #endif
 #ifndef SW_GROUPS_FUSE
-#define SW_GROUPS_FUSE 2
+#define SW_GROUPS_FUSE (-1)
 #endif
 __device__ __forceinline__ constexpr int sw_n_groups(int mode) { return mode < 0 ? 3 : mode; }
 // a warp's scheduler (SM sub-partition) is warp % 4
@@ -177,14 +177,16 @@ __global__ void __launch_bounds__(SW_THREADS, 1) k_symbols_w(const __grid_consta
     // and then everybody runs butterflies.  Groups of warps that are in step among themselves and apart from each other
     // overlap the phases at the price of one instruction stream per group; WHERE the groups sit matters (a warp's
     // scheduler is warp % 4), measured per 1024 TFs, compact layout:
-    //   one group                                                       0.461 ms
+    //                                                                    plain     with the FIR inside (FUSE)
+    //   one group                                                       0.456 ms   0.996 ms
     //   two groups, warps 0-5 / 6-11 (both streams on every sub-partition, round 2 first attempt)  slower than one
-    //   two groups on disjoint sub-partitions (bit 1 of the warp index)  0.430 ms
-    //   four groups, one per sub-partition                              0.440 ms
+    //   two groups on disjoint sub-partitions (bit 1 of the warp index)  0.417 ms   0.897 ms
+    //   four groups, one per sub-partition                              0.408 ms   0.882 ms
     //   three groups ACROSS the sub-partitions (warp / 4: every sub-partition hosts one warp of each group, so its
-    //   warps are in three different phases)                             0.397 ms   <- plain kernel
-    // With the FIR inside (FUSE) the order is reversed -- 0.953 ms across, 0.923 ms disjoint: the filter phase
-    // saturates the FP32 pipe of the sub-partitions it runs on whatever the others do.
+    //   warps are in three different phases)                             0.383 ms   0.876-0.884 ms   <- both kernels
+    // (profiles/r02_sw_groups_after_modifiers.txt.  Before the complex arithmetic moved to the packed instructions'
+    // operand modifiers -- 15 % more instructions -- the fused kernel preferred two disjoint groups: 0.923 against
+    // 0.945 ms, profiles/r02_sw_groups.txt.)
     constexpr int GMODE = FUSE ? SW_GROUPS_FUSE : SW_GROUPS_PLAIN;
     constexpr int SW_GROUPS = sw_n_groups(GMODE);
     constexpr int GRP_THREADS = SW_THREADS / SW_GROUPS;
